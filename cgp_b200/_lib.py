@@ -1,0 +1,250 @@
+"""ctypes binding of the C-ABI declared in include/cgp_b200.h.
+
+There is NO CPU fallback: importing this module without the built extension, or calling it without a
+CUDA device, raises.  Build with ``python -c "import __graft_entry__ as g; g.build()"``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(_HERE, "_cgp_b200.so")
+
+KIND = {"matern32": 0, "rbf": 1}
+
+_vp, _i64, _i32, _f64, _sz = C.c_void_p, C.c_int64, C.c_int32, C.c_double, C.c_size_t
+_pi64 = C.POINTER(C.c_int64)
+_pi32 = C.POINTER(C.c_int32)
+
+# name -> (restype, argtypes) — one entry per symbol of include/cgp_b200.h
+SIGNATURES = {
+    "cgp_version": (C.c_int, []),
+    "cgp_create": (C.c_int, [C.POINTER(_vp), C.c_int]),
+    "cgp_destroy": (C.c_int, [_vp]),
+    "cgp_padded_n": (_i64, [_i64]),
+    "cgp_model_elems": (_i64, [_pi64, C.c_int]),
+    "cgp_kernel_matrix": (C.c_int, [_vp, C.c_int, _vp, _i64, C.c_int, _vp, _f64, _vp, _vp]),
+    "cgp_kernel_cross": (C.c_int, [_vp, C.c_int, _vp, _i64, _vp, _i64, C.c_int, _vp, _vp, _vp]),
+    "cgp_lml_workspace_bytes": (_sz, [_pi64, C.c_int, _pi32, C.c_int, C.c_int]),
+    "cgp_lml_grad_batched": (C.c_int, [_vp, C.c_int, _vp, _vp, _pi64, C.c_int, C.c_int, _pi32, C.c_int, _vp, _f64,
+                                       _vp, _vp, _vp, _vp, _sz, _vp]),
+    "cgp_factorize_workspace_bytes": (_sz, [_pi64, C.c_int, C.c_int]),
+    "cgp_factorize": (C.c_int, [_vp, C.c_int, _vp, _vp, _pi64, C.c_int, C.c_int, _vp, _f64, _vp, _vp, _vp, _vp, _vp,
+                                _vp, _sz, _vp]),
+    "cgp_knn_labels": (C.c_int, [_vp, _vp, _vp, _i64, C.c_int, C.c_int, C.c_int, _vp, _i64, _vp, _vp]),
+    "cgp_score_workspace_bytes": (_sz, [_pi64, C.c_int, C.c_int, _i64]),
+    "cgp_predict": (C.c_int, [_vp, C.c_int, _vp, _pi64, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64,
+                              _vp, _vp, _vp, _sz, _vp]),
+    "cgp_ei_argmax": (C.c_int, [_vp, C.c_int, _vp, _pi64, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "cgp_dgemm_nt": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp]),
+}
+
+_lib = None
+_handles = {}
+
+
+class CgpError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load the shared library (no compute, usable without a GPU)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(SO_PATH):
+            raise CgpError(f"cgp_b200 CUDA extension not built: {SO_PATH} missing "
+                           "(run __graft_entry__.build()); there is no CPU fallback")
+        L = C.CDLL(SO_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def handle(device=None):
+    if not torch.cuda.is_available():
+        raise CgpError("cgp_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    dev = torch.cuda.current_device() if device is None else int(device)
+    if dev not in _handles:
+        h = _vp()
+        with torch.cuda.device(dev):
+            _chk(lib().cgp_create(C.byref(h), dev), "cgp_create")
+        _handles[dev] = h
+    return _handles[dev]
+
+
+def _chk(rc, what):
+    if rc != 0:
+        kind = f"argument {-rc} invalid" if rc < 0 else f"CUDA error {rc}"
+        raise CgpError(f"{what} failed: {kind}")
+
+
+def _ptr(t, dtype=torch.float64):
+    if t is None:
+        return None
+    if not (isinstance(t, torch.Tensor) and t.is_cuda and t.is_contiguous() and t.dtype == dtype):
+        raise CgpError(f"expected a contiguous CUDA tensor of dtype {dtype}, got "
+                       f"{type(t).__name__} {getattr(t, 'dtype', None)} {getattr(t, 'device', None)}")
+    return t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _host_i64(a):
+    a = np.ascontiguousarray(a, dtype=np.int64)
+    return a, a.ctypes.data_as(_pi64)
+
+
+def _host_i32(a):
+    a = np.ascontiguousarray(a, dtype=np.int32)
+    return a, a.ctypes.data_as(_pi32)
+
+
+def padded_n(n):
+    return int(lib().cgp_padded_n(int(n)))
+
+
+def model_elems(offs):
+    o, po = _host_i64(offs)
+    return int(lib().cgp_model_elems(po, len(o) - 1))
+
+
+# ------------------------------------------------------------------------------------------------
+def kernel_matrix(X, theta, kind="matern32", alpha=0.0):
+    n, d = X.shape
+    K = torch.empty((n, n), dtype=torch.float64, device=X.device)
+    _chk(lib().cgp_kernel_matrix(handle(X.device.index), KIND[kind], _ptr(X), n, d, _ptr(theta), float(alpha), _ptr(K),
+                                 _stream()), "cgp_kernel_matrix")
+    return K
+
+
+def kernel_cross(Q, X, theta, kind="matern32"):
+    m, d = Q.shape
+    n = X.shape[0]
+    K = torch.empty((m, n), dtype=torch.float64, device=X.device)
+    _chk(lib().cgp_kernel_cross(handle(X.device.index), KIND[kind], _ptr(Q), m, _ptr(X), n, d, _ptr(theta), _ptr(K),
+                                _stream()), "cgp_kernel_cross")
+    return K
+
+
+def dgemm_nt(A, B, out=None):
+    M, K = A.shape
+    N = B.shape[0]
+    Cm = out if out is not None else torch.empty((M, N), dtype=torch.float64, device=A.device)
+    _chk(lib().cgp_dgemm_nt(handle(A.device.index), _ptr(A), _ptr(B), _ptr(Cm), M, N, K, _stream()), "cgp_dgemm_nt")
+    return Cm
+
+
+def lml_workspace_bytes(offs, pair_cluster, d):
+    o, po = _host_i64(offs)
+    pc, ppc = _host_i32(pair_cluster)
+    return int(lib().cgp_lml_workspace_bytes(po, len(o) - 1, ppc, len(pc), d))
+
+
+def lml_grad_batched(X, y, offs, pair_cluster, theta, alpha, kind, workspace, want_grad=True):
+    """theta [B,P] CUDA -> (lml [B], grad [B,P] | None, info [B]) CUDA tensors (asynchronous)."""
+    o, po = _host_i64(offs)
+    pc, ppc = _host_i32(pair_cluster)
+    B, P = theta.shape
+    d = X.shape[1]
+    assert P == d + 1 and len(pc) == B
+    lml = torch.empty(B, dtype=torch.float64, device=X.device)
+    grad = torch.empty((B, P), dtype=torch.float64, device=X.device) if want_grad else None
+    info = torch.empty(B, dtype=torch.int32, device=X.device)
+    _chk(lib().cgp_lml_grad_batched(handle(X.device.index), KIND[kind], _ptr(X), _ptr(y), po, len(o) - 1, d, ppc, B,
+                                    _ptr(theta), float(alpha), _ptr(lml), _ptr(grad), _ptr(info, torch.int32),
+                                    _ptr(workspace, torch.uint8), workspace.numel(), _stream()),
+         "cgp_lml_grad_batched")
+    return lml, grad, info
+
+
+def factorize_workspace_bytes(offs, d):
+    o, po = _host_i64(offs)
+    return int(lib().cgp_factorize_workspace_bytes(po, len(o) - 1, d))
+
+
+def factorize(X, y, offs, theta, alpha, kind, workspace=None):
+    """theta [C,P] -> dict(L, W (padded layout), alpha_vec [n], lml [C], info [C])."""
+    o, po = _host_i64(offs)
+    Cn = len(o) - 1
+    d = X.shape[1]
+    elems = model_elems(o)
+    dev = X.device
+    L = torch.empty(elems, dtype=torch.float64, device=dev)
+    W = torch.empty(elems, dtype=torch.float64, device=dev)
+    av = torch.empty(X.shape[0], dtype=torch.float64, device=dev)
+    lml = torch.empty(Cn, dtype=torch.float64, device=dev)
+    info = torch.empty(Cn, dtype=torch.int32, device=dev)
+    if workspace is None:
+        workspace = torch.empty(factorize_workspace_bytes(o, d), dtype=torch.uint8, device=dev)
+    _chk(lib().cgp_factorize(handle(dev.index), KIND[kind], _ptr(X), _ptr(y), po, Cn, d, _ptr(theta), float(alpha),
+                             _ptr(L), _ptr(W), _ptr(av), _ptr(lml), _ptr(info, torch.int32),
+                             _ptr(workspace, torch.uint8), workspace.numel(), _stream()), "cgp_factorize")
+    return dict(L=L, W=W, alpha_vec=av, lml=lml, info=info)
+
+
+def knn_labels(X, labels, Q, k, n_classes):
+    n, d = X.shape
+    m = Q.shape[0]
+    out = torch.empty(m, dtype=torch.int64, device=X.device)
+    if m:
+        _chk(lib().cgp_knn_labels(handle(X.device.index), _ptr(X), _ptr(labels, torch.int64), n, d, int(k),
+                                  int(n_classes), _ptr(Q), m, _ptr(out, torch.int64), _stream()), "cgp_knn_labels")
+    return out
+
+
+def score_workspace_bytes(offs, d, m):
+    o, po = _host_i64(offs)
+    return int(lib().cgp_score_workspace_bytes(po, len(o) - 1, d, int(m)))
+
+
+def predict(X, offs, theta, W, alpha_vec, y_mean, y_std, Q, qlabel, kind, want_std=True, workspace=None):
+    o, po = _host_i64(offs)
+    d = X.shape[1]
+    m = Q.shape[0]
+    dev = X.device
+    mean = torch.empty(m, dtype=torch.float64, device=dev)
+    std = torch.empty(m, dtype=torch.float64, device=dev) if want_std else None
+    if m == 0:
+        return mean, std
+    if workspace is None:
+        workspace = torch.empty(score_workspace_bytes(o, d, m), dtype=torch.uint8, device=dev)
+    _chk(lib().cgp_predict(handle(dev.index), KIND[kind], _ptr(X), po, len(o) - 1, d, _ptr(theta), _ptr(W),
+                           _ptr(alpha_vec), _ptr(y_mean), _ptr(y_std), _ptr(Q), _ptr(qlabel, torch.int64), m,
+                           _ptr(mean), _ptr(std), _ptr(workspace, torch.uint8), workspace.numel(), _stream()),
+         "cgp_predict")
+    return mean, std
+
+
+def ei_argmax(X, offs, theta, W, alpha_vec, y_mean, y_std, y_max, Q, qlabel, kind, idx_base=0, want_arrays=False,
+              workspace=None):
+    """-> (best [score f64, idx i64, cluster i64] as CUDA tensors, score/mean/std arrays or None)."""
+    o, po = _host_i64(offs)
+    d = X.shape[1]
+    m = Q.shape[0]
+    dev = X.device
+    bs = torch.empty(1, dtype=torch.float64, device=dev)
+    bi = torch.empty(1, dtype=torch.int64, device=dev)
+    bc = torch.empty(1, dtype=torch.int64, device=dev)
+    score = mean = std = None
+    if want_arrays:
+        score = torch.empty(m, dtype=torch.float64, device=dev)
+        mean = torch.empty(m, dtype=torch.float64, device=dev)
+        std = torch.empty(m, dtype=torch.float64, device=dev)
+    if workspace is None:
+        workspace = torch.empty(score_workspace_bytes(o, d, m), dtype=torch.uint8, device=dev)
+    _chk(lib().cgp_ei_argmax(handle(dev.index), KIND[kind], _ptr(X), po, len(o) - 1, d, _ptr(theta), _ptr(W),
+                             _ptr(alpha_vec), _ptr(y_mean), _ptr(y_std), _ptr(y_max), _ptr(Q),
+                             _ptr(qlabel, torch.int64), m, int(idx_base), _ptr(score), _ptr(mean), _ptr(std),
+                             _ptr(bs), _ptr(bi, torch.int64), _ptr(bc, torch.int64), _ptr(workspace, torch.uint8),
+                             workspace.numel(), _stream()), "cgp_ei_argmax")
+    return (bs, bi, bc), (score, mean, std)

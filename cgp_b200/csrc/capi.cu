@@ -1,0 +1,592 @@
+// C-ABI of cgp_b200 (see include/cgp_b200.h).  Host-side orchestration only: every entry point is a
+// fixed sequence of asynchronous kernel launches on the caller's stream.
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "../../include/cgp_b200.h"
+#include "chol_diag.cuh"
+#include "common.cuh"
+#include "gemm_nt.cuh"
+#include "kernel_fn.cuh"
+#include "knn.cuh"
+#include "score.cuh"
+
+#define CGP_VERSION 100
+#define PINNED_BYTES (8u << 20)
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+static inline int64_t pad_n(int64_t n) { return (n + CGP_TILE - 1) / CGP_TILE * CGP_TILE; }
+
+struct HandleImpl : cgp_handle {
+    cudaEvent_t ring_event;
+    bool ring_event_pending;
+};
+
+template <typename K>
+static cudaError_t set_smem(K kernel, int bytes) {
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+}
+
+extern "C" int cgp_version(void) { return CGP_VERSION; }
+extern "C" int64_t cgp_padded_n(int64_t n) { return pad_n(n); }
+extern "C" int64_t cgp_model_elems(const int64_t* offs, int C) {
+    int64_t s = 0;
+    for (int c = 0; c < C; ++c) {
+        int64_t np = pad_n(offs[c + 1] - offs[c]);
+        s += np * np;
+    }
+    return s;
+}
+
+extern "C" int cgp_create(cgp_handle** out, int device) {
+    if (!out) return -1;
+    int cur = 0;
+    CGP_CHECK(cudaGetDevice(&cur));
+    if (cur != device) CGP_CHECK(cudaSetDevice(device));
+    HandleImpl* h = new (std::nothrow) HandleImpl();
+    if (!h) return (int)cudaErrorMemoryAllocation;
+    h->device = device;
+    CGP_CHECK(cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device));
+    CGP_CHECK(cudaMallocHost(&h->pinned, PINNED_BYTES));
+    h->pinned_bytes = PINNED_BYTES;
+    h->pinned_used = 0;
+    CGP_CHECK(cudaEventCreateWithFlags(&h->ring_event, cudaEventDisableTiming));
+    h->ring_event_pending = false;
+    CGP_CHECK(set_smem(k_dgemm_nt, GEMM_SMEM_BYTES));
+    CGP_CHECK(set_smem(k_potrf_update, GEMM_SMEM_BYTES));
+    CGP_CHECK(set_smem(k_potrf_panel, GEMM_SMEM_BYTES));
+    CGP_CHECK(set_smem(k_trtri_acc, GEMM_SMEM_BYTES));
+    CGP_CHECK(set_smem(k_trtri_scale, GEMM_SMEM_BYTES));
+    CGP_CHECK(set_smem(k_lauum, GEMM_SMEM_BYTES));
+    CGP_CHECK(set_smem(k_predict_vnorm, GEMM_SMEM_BYTES));
+    CGP_CHECK(set_smem(k_potrf_diag, DIAG_SMEM_BYTES));
+    *out = h;
+    return 0;
+}
+
+extern "C" int cgp_destroy(cgp_handle* hh) {
+    if (!hh) return -1;
+    HandleImpl* h = static_cast<HandleImpl*>(hh);
+    cudaEventDestroy(h->ring_event);
+    cudaFreeHost(h->pinned);
+    delete h;
+    return 0;
+}
+
+// Stage `bytes` of launch metadata through the pinned ring and copy it to `dst` on `s`.
+static int upload(HandleImpl* h, void* dst, const void* src, size_t bytes, cudaStream_t s) {
+    size_t need = align_up(bytes, 256);
+    if (need > h->pinned_bytes) return -100;
+    if (h->pinned_used + need > h->pinned_bytes) {
+        if (h->ring_event_pending) CGP_CHECK(cudaEventSynchronize(h->ring_event));
+        h->pinned_used = 0;
+    }
+    char* p = static_cast<char*>(h->pinned) + h->pinned_used;
+    memcpy(p, src, bytes);
+    h->pinned_used += need;
+    CGP_CHECK(cudaMemcpyAsync(dst, p, bytes, cudaMemcpyHostToDevice, s));
+    CGP_CHECK(cudaEventRecord(h->ring_event, s));
+    h->ring_event_pending = true;
+    return 0;
+}
+
+static inline int dmax_for(int d) { return d <= 4 ? 4 : (d <= 8 ? 8 : 16); }
+static inline size_t xtile_smem(int d) { return (size_t)2 * CGP_TILE * (d | 1) * 8; }
+
+// ------------------------------------------------------------------------------------------------
+// dense kernel matrices (K1 single-matrix form, cross kernel)
+// ------------------------------------------------------------------------------------------------
+static int launch_cross(int kind, const double* Q, int64_t m, const double* X, int64_t n, int d, const double* theta,
+                        double* out, int64_t ldo, int64_t rows_out, int64_t cols_out, int self, double alpha,
+                        cudaStream_t s) {
+    dim3 grid((unsigned)((cols_out + CGP_TILE - 1) / CGP_TILE), (unsigned)((rows_out + CGP_TILE - 1) / CGP_TILE));
+    if (grid.x == 0 || grid.y == 0) return 0;
+    size_t sm = xtile_smem(d);
+    if (kind == CGP_KIND_MATERN32)
+        k_cross<0><<<grid, 256, sm, s>>>(Q, m, X, n, d, theta, out, ldo, rows_out, cols_out, self, alpha);
+    else
+        k_cross<1><<<grid, 256, sm, s>>>(Q, m, X, n, d, theta, out, ldo, rows_out, cols_out, self, alpha);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int cgp_kernel_matrix(cgp_handle* h, int kind, const double* X, int64_t n, int d, const double* theta,
+                                 double alpha, double* K, void* stream) {
+    if (!h) return -1;
+    if (kind != 0 && kind != 1) return -2;
+    if (!X || n < 0) return -3;
+    if (d < 1 || d > CGP_MAX_D) return -5;
+    if (!theta) return -6;
+    if (!K) return -8;
+    return launch_cross(kind, X, n, X, n, d, theta, K, n, n, n, 1, alpha, (cudaStream_t)stream);
+}
+
+extern "C" int cgp_kernel_cross(cgp_handle* h, int kind, const double* Q, int64_t m, const double* X, int64_t n, int d,
+                                const double* theta, double* Kqx, void* stream) {
+    if (!h) return -1;
+    if (kind != 0 && kind != 1) return -2;
+    if (!Q || m < 0) return -3;
+    if (!X || n < 0) return -5;
+    if (d < 1 || d > CGP_MAX_D) return -7;
+    if (!theta) return -8;
+    if (!Kqx) return -9;
+    return launch_cross(kind, Q, m, X, n, d, theta, Kqx, n, m, n, 0, 0.0, (cudaStream_t)stream);
+}
+
+extern "C" int cgp_dgemm_nt(cgp_handle* h, const double* A, const double* B, double* C, int64_t M, int64_t N, int64_t K,
+                            void* stream) {
+    if (!h) return -1;
+    if (!A || !B || !C) return -2;
+    if (M <= 0 || M % CGP_TILE || N <= 0 || N % CGP_TILE || K <= 0 || K % CGP_BK) return -5;
+    dim3 grid((unsigned)(N / CGP_TILE), (unsigned)(M / CGP_TILE));
+    k_dgemm_nt<<<grid, CGP_GEMM_THREADS, GEMM_SMEM_BYTES, (cudaStream_t)stream>>>(A, B, C, M, N, (int)K);
+    return (int)cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// batched factorisation pipeline
+// ------------------------------------------------------------------------------------------------
+struct Batch {
+    int nm = 0, Tmax = 0, npad_max = 0, ntl_max = 0;
+    MatMeta* meta = nullptr;  // device
+    double *A = nullptr, *U = nullptr, *D = nullptr, *logdet = nullptr, *z = nullptr, *a = nullptr, *gpart = nullptr;
+};
+
+// assemble -> blocked Cholesky -> U = L^-T -> z, a, lml [-> K^-1 -> gradient]
+static int run_pipeline(int kind, const double* X, const double* y, const double* theta, double alpha, int d,
+                        const Batch& b, double* lml, double* grad, int* info, cudaStream_t s) {
+    const int nm = b.nm, T = b.Tmax;
+    const size_t xs = xtile_smem(d);
+    dim3 gl(b.ntl_max, nm);
+    if (kind == 0)
+        k_assemble<0><<<gl, 256, xs, s>>>(b.A, X, theta, b.meta, d, alpha);
+    else
+        k_assemble<1><<<gl, 256, xs, s>>>(b.A, X, theta, b.meta, d, alpha);
+    for (int j = 0; j < T; ++j) {
+        if (j > 0) k_potrf_update<<<dim3(T - j, nm), CGP_GEMM_THREADS, GEMM_SMEM_BYTES, s>>>(b.A, b.meta, j);
+        k_potrf_diag<<<nm, 256, DIAG_SMEM_BYTES, s>>>(b.A, b.U, b.D, b.logdet, info, b.meta, j, T);
+        if (j + 1 < T) k_potrf_panel<<<dim3(T - j - 1, nm), CGP_GEMM_THREADS, GEMM_SMEM_BYTES, s>>>(b.A, b.D, b.meta, j);
+    }
+    for (int i = 1; i < T; ++i) {
+        k_trtri_acc<<<dim3(i, nm), CGP_GEMM_THREADS, GEMM_SMEM_BYTES, s>>>(b.A, b.U, b.meta, i);
+        k_trtri_scale<<<dim3(i, nm), CGP_GEMM_THREADS, GEMM_SMEM_BYTES, s>>>(b.U, b.D, b.meta, i);
+    }
+    k_solve_z<<<dim3(T, nm), 128, 0, s>>>(b.U, y, b.z, b.meta, b.npad_max);
+    k_solve_a<<<dim3(b.npad_max / 8, nm), 256, 0, s>>>(b.U, b.z, b.a, b.meta, b.npad_max);
+    k_lml_finish<<<nm, 256, 0, s>>>(b.z, b.logdet, info, lml, b.meta, b.npad_max, T);
+    if (grad) {
+        k_lauum<<<gl, CGP_GEMM_THREADS, GEMM_SMEM_BYTES, s>>>(b.A, b.U, b.meta);
+        const int dm = dmax_for(d);
+        const size_t gs = xs + (2 * CGP_TILE + 8 * dm) * 8;
+#define LAUNCH_GRAD(KIND, DM)                                                                                        \
+    k_grad_tiles<KIND, DM><<<gl, 256, gs, s>>>(b.A, X, b.a, theta, b.gpart, b.meta, d, b.npad_max, b.ntl_max);       \
+    k_grad_finish<DM><<<nm, 256, 0, s>>>(b.A, b.a, b.gpart, theta, info, grad, b.meta, d, b.npad_max, b.ntl_max)
+        if (kind == 0) {
+            if (dm == 4) { LAUNCH_GRAD(0, 4); } else if (dm == 8) { LAUNCH_GRAD(0, 8); } else { LAUNCH_GRAD(0, 16); }
+        } else {
+            if (dm == 4) { LAUNCH_GRAD(1, 4); } else if (dm == 8) { LAUNCH_GRAD(1, 8); } else { LAUNCH_GRAD(1, 16); }
+        }
+#undef LAUNCH_GRAD
+    }
+    return (int)cudaGetLastError();
+}
+
+// Carve the batch buffers for mats [m0, m1) out of ws.  Returns bytes used, or 0 if it does not fit.
+static size_t carve(char* ws, size_t ws_bytes, const std::vector<MatMeta>& metas, int m0, int m1, int d, bool with_A,
+                    Batch& b) {
+    int nm = m1 - m0, npmax = 0;
+    size_t a_el = 0, d_el = 0;
+    for (int i = m0; i < m1; ++i) {
+        npmax = std::max(npmax, metas[i].npad);
+        a_el += (size_t)metas[i].npad * metas[i].npad;
+        d_el += (size_t)metas[i].npad * CGP_TILE;
+    }
+    int T = npmax / CGP_TILE, ntl = T * (T + 1) / 2;
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        size_t o = off;
+        off = align_up(off + bytes, 256);
+        return o;
+    };
+    size_t o_meta = take((size_t)nm * sizeof(MatMeta));
+    size_t o_A = with_A ? take(a_el * 8) : 0;
+    size_t o_U = take(a_el * 8);
+    size_t o_D = take(d_el * 8);
+    size_t o_ld = take((size_t)nm * T * 8);
+    size_t o_z = take((size_t)nm * npmax * 8);
+    size_t o_a = take((size_t)nm * npmax * 8);
+    size_t o_g = take((size_t)nm * ntl * dmax_for(d) * 8);
+    if (off > ws_bytes) return 0;
+    b.nm = nm;
+    b.Tmax = T;
+    b.npad_max = npmax;
+    b.ntl_max = ntl;
+    b.meta = reinterpret_cast<MatMeta*>(ws + o_meta);
+    b.A = with_A ? reinterpret_cast<double*>(ws + o_A) : nullptr;
+    b.U = reinterpret_cast<double*>(ws + o_U);
+    b.D = reinterpret_cast<double*>(ws + o_D);
+    b.logdet = reinterpret_cast<double*>(ws + o_ld);
+    b.z = reinterpret_cast<double*>(ws + o_z);
+    b.a = reinterpret_cast<double*>(ws + o_a);
+    b.gpart = reinterpret_cast<double*>(ws + o_g);
+    return off;
+}
+
+static size_t batch_bytes(const std::vector<MatMeta>& metas, int m0, int m1, int d, bool with_A) {
+    Batch b;
+    return carve(nullptr, (size_t)-1, metas, m0, m1, d, with_A, b);
+}
+
+extern "C" size_t cgp_lml_workspace_bytes(const int64_t* offs, int C, const int32_t* pair_cluster, int B, int d) {
+    if (!offs || !pair_cluster || B <= 0) return 0;
+    std::vector<MatMeta> metas(B);
+    for (int i = 0; i < B; ++i) {
+        int c = pair_cluster[i];
+        if (c < 0 || c >= C) return 0;
+        metas[i].n = (int)(offs[c + 1] - offs[c]);
+        metas[i].npad = (int)pad_n(metas[i].n);
+    }
+    return batch_bytes(metas, 0, B, d, true);
+}
+
+extern "C" int cgp_lml_grad_batched(cgp_handle* hh, int kind, const double* X, const double* y, const int64_t* offs,
+                                    int C, int d, const int32_t* pair_cluster, int B, const double* theta, double alpha,
+                                    double* lml, double* grad, int32_t* info, void* workspace, size_t ws_bytes,
+                                    void* stream) {
+    HandleImpl* h = static_cast<HandleImpl*>(hh);
+    if (!h) return -1;
+    if (kind != 0 && kind != 1) return -2;
+    if (!X) return -3;
+    if (!y) return -4;
+    if (!offs || C <= 0) return -5;
+    if (d < 1 || d > CGP_MAX_D) return -7;
+    if (!pair_cluster || B < 0) return -8;
+    if (!theta) return -10;
+    if (!lml) return -12;
+    if (!info) return -14;
+    if (!workspace) return -15;
+    if (B == 0) return 0;
+    cudaStream_t s = (cudaStream_t)stream;
+    std::vector<MatMeta> metas(B);
+    for (int i = 0; i < B; ++i) {
+        int c = pair_cluster[i];
+        if (c < 0 || c >= C) return -8;
+        MatMeta& m = metas[i];
+        m.n = (int)(offs[c + 1] - offs[c]);
+        if (m.n <= 0) return -5;
+        m.npad = (int)pad_n(m.n);
+        m.xoff = (int)offs[c];
+        m.theta_idx = i;
+        m.out_idx = i;
+        m.pad_ = 0;
+    }
+    CGP_CHECK(cudaMemsetAsync(info, 0, (size_t)B * sizeof(int32_t), s));
+    // process the pairs in as few chunks as the workspace allows
+    int m0 = 0;
+    while (m0 < B) {
+        int m1 = m0 + 1;
+        if (batch_bytes(metas, m0, m1, d, true) > ws_bytes) return -16;
+        // grow geometrically then linearly
+        int lo = m1, hi = B;
+        while (lo < hi) {
+            int mid = (lo + hi + 1) / 2;
+            if (batch_bytes(metas, m0, mid, d, true) <= ws_bytes) lo = mid; else hi = mid - 1;
+        }
+        m1 = lo;
+        Batch b;
+        carve(static_cast<char*>(workspace), ws_bytes, metas, m0, m1, d, true, b);
+        long long ao = 0, dof = 0;
+        for (int i = m0; i < m1; ++i) {
+            metas[i].a_off = ao;
+            metas[i].u_off = ao;
+            metas[i].d_off = dof;
+            ao += (long long)metas[i].npad * metas[i].npad;
+            dof += (long long)metas[i].npad * CGP_TILE;
+        }
+        int rc = upload(h, b.meta, &metas[m0], (size_t)(m1 - m0) * sizeof(MatMeta), s);
+        if (rc) return rc;
+        rc = run_pipeline(kind, X, y, theta, alpha, d, b, lml, grad, info, s);
+        if (rc) return rc;
+        m0 = m1;
+    }
+    return 0;
+}
+
+// copy a (per-matrix strided scratch) into the cluster-sorted alpha vector
+__global__ void k_gather_alpha(const double* __restrict__ abuf, double* __restrict__ alpha_vec, const MatMeta* __restrict__ meta,
+                               int zstride) {
+    const MatMeta m = meta[blockIdx.y];
+    int i = blockIdx.x * 256 + threadIdx.x;
+    if (i < m.n) alpha_vec[m.xoff + i] = abuf[(long long)blockIdx.y * zstride + i];
+}
+
+static void cluster_metas(const int64_t* offs, int C, std::vector<MatMeta>& metas) {
+    metas.resize(C);
+    long long ao = 0, dof = 0;
+    for (int c = 0; c < C; ++c) {
+        MatMeta& m = metas[c];
+        m.n = (int)(offs[c + 1] - offs[c]);
+        m.npad = (int)pad_n(m.n);
+        m.xoff = (int)offs[c];
+        m.theta_idx = c;
+        m.out_idx = c;
+        m.pad_ = 0;
+        m.a_off = ao;
+        m.u_off = ao;
+        m.d_off = dof;
+        ao += (long long)m.npad * m.npad;
+        dof += (long long)m.npad * CGP_TILE;
+    }
+}
+
+extern "C" size_t cgp_factorize_workspace_bytes(const int64_t* offs, int C, int d) {
+    if (!offs || C <= 0) return 0;
+    std::vector<MatMeta> metas;
+    cluster_metas(offs, C, metas);
+    return batch_bytes(metas, 0, C, d, false);
+}
+
+extern "C" int cgp_factorize(cgp_handle* hh, int kind, const double* X, const double* y, const int64_t* offs, int C, int d,
+                             const double* theta, double alpha, double* L, double* W, double* alpha_vec, double* lml,
+                             int32_t* info, void* workspace, size_t ws_bytes, void* stream) {
+    HandleImpl* h = static_cast<HandleImpl*>(hh);
+    if (!h) return -1;
+    if (kind != 0 && kind != 1) return -2;
+    if (!X) return -3;
+    if (!y) return -4;
+    if (!offs || C <= 0) return -5;
+    if (d < 1 || d > CGP_MAX_D) return -7;
+    if (!theta) return -8;
+    if (!L) return -10;
+    if (!W) return -11;
+    if (!alpha_vec) return -12;
+    if (!lml) return -13;
+    if (!info) return -14;
+    if (!workspace) return -15;
+    cudaStream_t s = (cudaStream_t)stream;
+    std::vector<MatMeta> metas;
+    cluster_metas(offs, C, metas);
+    for (int c = 0; c < C; ++c)
+        if (metas[c].n <= 0) return -5;
+    Batch b;
+    if (carve(static_cast<char*>(workspace), ws_bytes, metas, 0, C, d, false, b) == 0) return -16;
+    b.A = L;
+    CGP_CHECK(cudaMemsetAsync(info, 0, (size_t)C * sizeof(int32_t), s));
+    int64_t elems = cgp_model_elems(offs, C);
+    CGP_CHECK(cudaMemsetAsync(b.U, 0, (size_t)elems * 8, s));
+    int rc = upload(h, b.meta, metas.data(), (size_t)C * sizeof(MatMeta), s);
+    if (rc) return rc;
+    rc = run_pipeline(kind, X, y, theta, alpha, d, b, lml, nullptr, info, s);
+    if (rc) return rc;
+    k_transpose<<<dim3(b.npad_max / 32, b.npad_max / 32, C), dim3(32, 8), 0, s>>>(b.U, W, b.meta);
+    k_gather_alpha<<<dim3((b.npad_max + 255) / 256, C), 256, 0, s>>>(b.a, alpha_vec, b.meta, b.npad_max);
+    return (int)cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// k-NN routing
+// ------------------------------------------------------------------------------------------------
+template <int D>
+static int launch_knn(const double* X, const long long* lab, int n, int k, const double* Q, long long M, long long* out,
+                      cudaStream_t s) {
+    size_t sm = (size_t)KNN_TILE * D * 8 + KNN_TILE * 4;
+    if (sm > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(k_knn<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        if (e != cudaSuccess) return (int)e;
+    }
+    unsigned grid = (unsigned)((M + KNN_THREADS - 1) / KNN_THREADS);
+    k_knn<D><<<grid, KNN_THREADS, sm, s>>>(X, lab, n, k, Q, M, out);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int cgp_knn_labels(cgp_handle* h, const double* X, const int64_t* labels, int64_t n, int d, int k, int n_classes,
+                              const double* Q, int64_t m, int64_t* out, void* stream) {
+    if (!h) return -1;
+    if (!X) return -2;
+    if (!labels) return -3;
+    if (n <= 0 || n > 0x7fffffff) return -4;
+    if (d < 1 || d > CGP_MAX_D) return -5;
+    if (k < 1 || k > CGP_MAX_K || k > n) return -6;
+    if (n_classes < 1) return -7;
+    if (m < 0) return -9;
+    if (m == 0) return 0;
+    if (!Q) return -8;
+    if (!out) return -10;
+    cudaStream_t s = (cudaStream_t)stream;
+    const long long* lab = reinterpret_cast<const long long*>(labels);
+    long long* o = reinterpret_cast<long long*>(out);
+    switch (d) {
+#define KNN_CASE(D) \
+    case D:         \
+        return launch_knn<D>(X, lab, (int)n, k, Q, m, o, s);
+        KNN_CASE(1) KNN_CASE(2) KNN_CASE(3) KNN_CASE(4) KNN_CASE(5) KNN_CASE(6) KNN_CASE(7) KNN_CASE(8)
+        KNN_CASE(9) KNN_CASE(10) KNN_CASE(11) KNN_CASE(12) KNN_CASE(13) KNN_CASE(14) KNN_CASE(15) KNN_CASE(16)
+#undef KNN_CASE
+    }
+    return -5;
+}
+
+// ------------------------------------------------------------------------------------------------
+// routed prediction / EI scan
+// ------------------------------------------------------------------------------------------------
+struct ScoreLayout {
+    int64_t mch;  // candidates per chunk (multiple of 128)
+    int nblk, Tmax;
+    int64_t npad_max;
+    size_t o_perm, o_qs, o_sorted, o_hist, o_blkoff, o_coff, o_blkv, o_blkp, o_kstar, o_vpart, o_mraw, total;
+};
+
+static ScoreLayout score_layout(const int64_t* offs, int C, int d, int64_t m) {
+    ScoreLayout L;
+    L.npad_max = 0;
+    for (int c = 0; c < C; ++c) L.npad_max = std::max<int64_t>(L.npad_max, pad_n(offs[c + 1] - offs[c]));
+    L.Tmax = (int)(L.npad_max / CGP_TILE);
+    int64_t mch = ((int64_t)1 << 27) / std::max<int64_t>(L.npad_max, 1);
+    mch = std::max<int64_t>(CGP_TILE, std::min<int64_t>(mch, 65536));
+    mch = mch / CGP_TILE * CGP_TILE;
+    mch = std::min<int64_t>(mch, pad_n(std::max<int64_t>(m, 1)));
+    L.mch = mch;
+    L.nblk = (int)((m + BUCKET_CH - 1) / BUCKET_CH);
+    if (L.nblk < 1) L.nblk = 1;
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        size_t o = off;
+        off = align_up(off + bytes, 256);
+        return o;
+    };
+    L.o_perm = take((size_t)m * 8);
+    L.o_qs = take((size_t)m * d * 8);
+    L.o_sorted = take((size_t)m * 8);
+    L.o_hist = take((size_t)C * L.nblk * 4);
+    L.o_blkoff = take((size_t)C * L.nblk * 8);
+    L.o_coff = take((size_t)(C + 1) * 8);
+    L.o_blkv = take(1024 * 8);
+    L.o_blkp = take(1024 * 8);
+    L.o_kstar = take((size_t)mch * L.npad_max * 8);
+    L.o_vpart = take((size_t)L.Tmax * mch * 8);
+    L.o_mraw = take((size_t)mch * 8);
+    L.total = off;
+    return L;
+}
+
+extern "C" size_t cgp_score_workspace_bytes(const int64_t* offs, int C, int d, int64_t m) {
+    if (!offs || C <= 0 || m < 0) return 0;
+    return score_layout(offs, C, d, m).total;
+}
+
+static int run_score(HandleImpl* h, int kind, const double* X, const int64_t* offs, int C, int d, const double* theta,
+                     const double* W, const double* alpha_vec, const double* y_mean, const double* y_std,
+                     const double* y_max, const double* Q, const int64_t* qlabel, int64_t m, int64_t idx_base,
+                     double* score, double* mean, double* std_, double* best_score, int64_t* best_idx,
+                     int64_t* best_cluster, void* workspace, size_t ws_bytes, cudaStream_t s) {
+    if (C > 4096) return -5;
+    ScoreLayout L = score_layout(offs, C, d, m);
+    if (L.total > ws_bytes) return -100;
+    char* ws = static_cast<char*>(workspace);
+    long long* perm = reinterpret_cast<long long*>(ws + L.o_perm);
+    double* Qs = reinterpret_cast<double*>(ws + L.o_qs);
+    double* sorted = reinterpret_cast<double*>(ws + L.o_sorted);
+    int* hist = reinterpret_cast<int*>(ws + L.o_hist);
+    long long* blkoff = reinterpret_cast<long long*>(ws + L.o_blkoff);
+    long long* coff = reinterpret_cast<long long*>(ws + L.o_coff);
+    double* blkv = reinterpret_cast<double*>(ws + L.o_blkv);
+    long long* blkp = reinterpret_cast<long long*>(ws + L.o_blkp);
+    double* kstar = reinterpret_cast<double*>(ws + L.o_kstar);
+    double* vpart = reinterpret_cast<double*>(ws + L.o_vpart);
+    double* mraw = reinterpret_cast<double*>(ws + L.o_mraw);
+    const long long* ql = reinterpret_cast<const long long*>(qlabel);
+
+    k_bucket_hist<<<L.nblk, 256, (size_t)C * 4, s>>>(ql, m, C, L.nblk, hist);
+    k_bucket_scan<<<1, 1024, 0, s>>>(hist, blkoff, coff, C, L.nblk);
+    k_bucket_scatter<<<L.nblk, 32, (size_t)C * 8, s>>>(ql, Q, m, C, L.nblk, d, blkoff, perm, Qs);
+    CGP_CHECK(cudaGetLastError());
+    std::vector<long long> hoff(C + 1);
+    CGP_CHECK(cudaMemcpyAsync(hoff.data(), coff, (size_t)(C + 1) * 8, cudaMemcpyDeviceToHost, s));
+    CGP_CHECK(cudaStreamSynchronize(s));  // launch geometry of the per-cluster chunks depends on the counts
+
+    const int P = d + 1;
+    long long woff = 0;
+    for (int c = 0; c < C; ++c) {
+        const int64_t n = offs[c + 1] - offs[c];
+        const int64_t npad = pad_n(n);
+        const int T = (int)(npad / CGP_TILE);
+        const double* Wc = W + woff;
+        woff += npad * npad;
+        const double* th = theta + (long long)c * P;
+        const double* Xc = X + offs[c] * d;
+        for (long long p0 = hoff[c]; p0 < hoff[c + 1]; p0 += L.mch) {
+            const long long rows = std::min<long long>(L.mch, hoff[c + 1] - p0);
+            const long long rows_pad = pad_n(rows);
+            int rc = launch_cross(kind, Qs + p0 * d, rows, Xc, n, d, th, kstar, npad, rows_pad, npad, 0, 0.0, s);
+            if (rc) return rc;
+            k_mean<<<(unsigned)((rows + 7) / 8), 256, 0, s>>>(kstar, alpha_vec + offs[c], (int)n, (int)npad, rows, mraw);
+            k_predict_vnorm<<<(unsigned)((rows_pad / CGP_TILE) * T), CGP_GEMM_THREADS, GEMM_SMEM_BYTES, s>>>(
+                Wc, kstar, vpart, (int)npad, L.mch);
+            k_score_finish<<<(unsigned)((rows + 255) / 256), 256, 0, s>>>(vpart, L.mch, T, mraw, rows, p0, perm, th, d,
+                                                                          y_mean, y_std, y_max, c, 0.0, (double)n, mean,
+                                                                          std_, score, sorted);
+        }
+    }
+    if (y_max && best_score && best_idx && best_cluster) {
+        int nb = (int)std::min<long long>(1024, (m + 255) / 256);
+        if (nb < 1) nb = 1;
+        k_argmax_blocks<<<nb, 256, 0, s>>>(sorted, m, blkv, blkp);
+        k_argmax_final<<<1, 256, 0, s>>>(blkv, blkp, nb, perm, coff, C, idx_base, best_score, reinterpret_cast<long long*>(best_idx),
+                                         reinterpret_cast<long long*>(best_cluster));
+    }
+    return (int)cudaGetLastError();
+}
+
+extern "C" int cgp_predict(cgp_handle* hh, int kind, const double* X, const int64_t* offs, int C, int d, const double* theta,
+                           const double* W, const double* alpha_vec, const double* y_mean, const double* y_std,
+                           const double* Q, const int64_t* qlabel, int64_t m, double* mean, double* std_, void* workspace,
+                           size_t ws_bytes, void* stream) {
+    HandleImpl* h = static_cast<HandleImpl*>(hh);
+    if (!h) return -1;
+    if (kind != 0 && kind != 1) return -2;
+    if (!X) return -3;
+    if (!offs || C <= 0) return -4;
+    if (d < 1 || d > CGP_MAX_D) return -6;
+    if (!theta) return -7;
+    if (!W) return -8;
+    if (!alpha_vec) return -9;
+    if (!y_mean) return -10;
+    if (!y_std) return -11;
+    if (m < 0) return -14;
+    if (m == 0) return 0;
+    if (!Q) return -12;
+    if (!qlabel) return -13;
+    if (!mean) return -15;
+    if (!workspace) return -17;
+    return run_score(h, kind, X, offs, C, d, theta, W, alpha_vec, y_mean, y_std, nullptr, Q, qlabel, m, 0, nullptr, mean,
+                     std_, nullptr, nullptr, nullptr, workspace, ws_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int cgp_ei_argmax(cgp_handle* hh, int kind, const double* X, const int64_t* offs, int C, int d,
+                             const double* theta, const double* W, const double* alpha_vec, const double* y_mean,
+                             const double* y_std, const double* y_max, const double* Q, const int64_t* qlabel, int64_t m,
+                             int64_t idx_base, double* score, double* mean, double* std_, double* best_score,
+                             int64_t* best_idx, int64_t* best_cluster, void* workspace, size_t ws_bytes, void* stream) {
+    HandleImpl* h = static_cast<HandleImpl*>(hh);
+    if (!h) return -1;
+    if (kind != 0 && kind != 1) return -2;
+    if (!X) return -3;
+    if (!offs || C <= 0) return -4;
+    if (d < 1 || d > CGP_MAX_D) return -6;
+    if (!theta) return -7;
+    if (!W) return -8;
+    if (!alpha_vec) return -9;
+    if (!y_mean) return -10;
+    if (!y_std) return -11;
+    if (!y_max) return -12;
+    if (m <= 0) return -15;
+    if (!Q) return -13;
+    if (!qlabel) return -14;
+    if (!best_score) return -20;
+    if (!best_idx) return -21;
+    if (!best_cluster) return -22;
+    if (!workspace) return -23;
+    return run_score(h, kind, X, offs, C, d, theta, W, alpha_vec, y_mean, y_std, y_max, Q, qlabel, m, idx_base, score, mean,
+                     std_, best_score, best_idx, best_cluster, workspace, ws_bytes, (cudaStream_t)stream);
+}

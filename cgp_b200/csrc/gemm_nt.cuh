@@ -1,0 +1,269 @@
+// fp64 tensor-core (DMMA) tile GEMM, "NT" form:  acc[128x128] = sum_k A[m,k] * B[n,k]
+// Both operands are row-major with k contiguous.  Every blocked step of the factorisation
+// (left-looking Cholesky update, panel scaling by an inverted diagonal block, triangular inverse,
+// U U^T, and the predictive-variance contraction W k*) is phrased in this one form, so there is a
+// single mainloop: cp.async 4-stage ring -> swizzled shared tiles -> LDS.128 fragment loads ->
+// mma.sync.m8n8k4.f64.
+#pragma once
+#include "common.cuh"
+
+// One pipeline stage: A tile [128][16] + B tile [128][16] doubles (128 B per row = 8 chunks of 16 B).
+// Chunk c of row r lives at physical chunk c ^ ((r & 1) << 2): the 8 lanes of a quarter-warp
+// (rows r, r+1; 4 chunks each) then cover 128 distinct bytes -> conflict-free LDS.128.
+#define GEMM_TILE_ELEMS (CGP_TILE * CGP_BK)
+#define GEMM_SMEM_BYTES (CGP_STAGES * 2 * GEMM_TILE_ELEMS * 8)
+
+__device__ __forceinline__ int gemm_swz(int row, int chunk) { return chunk ^ ((row & 1) << 2); }
+
+__device__ __forceinline__ void gemm_load_stage(double* sa, double* sb, const double* __restrict__ gA,
+                                                long long lda, const double* __restrict__ gB,
+                                                long long ldb, int k0, int tid) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        int idx = tid + i * CGP_GEMM_THREADS;
+        int row = idx >> 3, c = idx & 7;
+        int pc = gemm_swz(row, c) * 2;
+        cp_async16(sa + row * CGP_BK + pc, gA + (long long)row * lda + k0 + c * 2);
+        cp_async16(sb + row * CGP_BK + pc, gB + (long long)row * ldb + k0 + c * 2);
+    }
+}
+
+// acc[mt][nt][e]: row = wm*64 + mt*8 + g, col = wn*32 + nt*8 + 2*t + e   (g = lane>>2, t = lane&3)
+struct GemmAcc {
+    double v[8][4][2];
+};
+
+__device__ __forceinline__ void gemm_zero(GemmAcc& acc) {
+#pragma unroll
+    for (int mt = 0; mt < 8; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) acc.v[mt][nt][0] = acc.v[mt][nt][1] = 0.0;
+}
+
+// K must be a positive multiple of CGP_BK.  smem: GEMM_SMEM_BYTES, 16-byte aligned.
+__device__ __forceinline__ void gemm_mainloop(GemmAcc& acc, double* smem, const double* __restrict__ gA,
+                                              long long lda, const double* __restrict__ gB,
+                                              long long ldb, int K) {
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int wm = warp & 1, wn = warp >> 1;
+    const int g = lane >> 2, t = lane & 3;
+    double* sA = smem;
+    double* sB = smem + CGP_STAGES * GEMM_TILE_ELEMS;
+    const int nk = K / CGP_BK;
+
+#pragma unroll
+    for (int s = 0; s < CGP_STAGES - 1; ++s) {
+        if (s < nk) gemm_load_stage(sA + s * GEMM_TILE_ELEMS, sB + s * GEMM_TILE_ELEMS, gA, lda, gB, ldb, s * CGP_BK, tid);
+        cp_async_commit();
+    }
+    for (int kt = 0; kt < nk; ++kt) {
+        cp_async_wait<CGP_STAGES - 2>();
+        __syncthreads();
+        {
+            int nx = kt + CGP_STAGES - 1;
+            if (nx < nk) {
+                int slot = nx % CGP_STAGES;
+                gemm_load_stage(sA + slot * GEMM_TILE_ELEMS, sB + slot * GEMM_TILE_ELEMS, gA, lda, gB, ldb, nx * CGP_BK, tid);
+            }
+            cp_async_commit();
+        }
+        const double* a_s = sA + (kt % CGP_STAGES) * GEMM_TILE_ELEMS;
+        const double* b_s = sB + (kt % CGP_STAGES) * GEMM_TILE_ELEMS;
+#pragma unroll
+        for (int kk = 0; kk < 2; ++kk) {
+            double2 af[8], bf[4];
+#pragma unroll
+            for (int mt = 0; mt < 8; ++mt) {
+                int row = wm * 64 + mt * 8 + g;
+                af[mt] = *reinterpret_cast<const double2*>(a_s + row * CGP_BK + gemm_swz(row, kk * 4 + t) * 2);
+            }
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+                int row = wn * 32 + nt * 8 + g;
+                bf[nt] = *reinterpret_cast<const double2*>(b_s + row * CGP_BK + gemm_swz(row, kk * 4 + t) * 2);
+            }
+            // k-slot s of the first DMMA is k = 2s, of the second k = 2s+1 (same permutation in A and B)
+#pragma unroll
+            for (int mt = 0; mt < 8; ++mt)
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt) {
+                    dmma884(acc.v[mt][nt][0], acc.v[mt][nt][1], af[mt].x, bf[nt].x);
+                    dmma884(acc.v[mt][nt][0], acc.v[mt][nt][1], af[mt].y, bf[nt].y);
+                }
+        }
+    }
+    cp_async_wait<0>();
+    __syncthreads();
+}
+
+// ---- epilogues -------------------------------------------------------------------------------
+// C[row, col] (row-major, ldc) op= acc.   MODE 0: C = acc   1: C = -acc   2: C -= acc
+template <int MODE>
+__device__ __forceinline__ void gemm_store(const GemmAcc& acc, double* __restrict__ C, long long ldc) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int wm = warp & 1, wn = warp >> 1, g = lane >> 2, t = lane & 3;
+#pragma unroll
+    for (int mt = 0; mt < 8; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+            int row = wm * 64 + mt * 8 + g, col = wn * 32 + nt * 8 + 2 * t;
+            double2* p = reinterpret_cast<double2*>(C + (long long)row * ldc + col);
+            double2 o;
+            if (MODE == 0) {
+                o.x = acc.v[mt][nt][0];
+                o.y = acc.v[mt][nt][1];
+            } else if (MODE == 1) {
+                o.x = -acc.v[mt][nt][0];
+                o.y = -acc.v[mt][nt][1];
+            } else {
+                o = *p;
+                o.x -= acc.v[mt][nt][0];
+                o.y -= acc.v[mt][nt][1];
+            }
+            *p = o;
+        }
+}
+
+// out[col] = sum over the 128 rows of acc^2 (fixed summation order -> bit-reproducible).
+// red: shared scratch of 2*128 doubles.
+__device__ __forceinline__ void gemm_colsumsq(const GemmAcc& acc, double* red, double* __restrict__ out) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int wm = warp & 1, wn = warp >> 1, g = lane >> 2, t = lane & 3;
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            double s = 0.0;
+#pragma unroll
+            for (int mt = 0; mt < 8; ++mt) s += acc.v[mt][nt][e] * acc.v[mt][nt][e];
+            s += __shfl_xor_sync(0xffffffffu, s, 4);
+            s += __shfl_xor_sync(0xffffffffu, s, 8);
+            s += __shfl_xor_sync(0xffffffffu, s, 16);
+            if (g == 0) red[wm * CGP_TILE + wn * 32 + nt * 8 + 2 * t + e] = s;
+        }
+    __syncthreads();
+    if (threadIdx.x < CGP_TILE) out[threadIdx.x] = red[threadIdx.x] + red[CGP_TILE + threadIdx.x];
+}
+
+// ---- kernels ---------------------------------------------------------------------------------
+extern __shared__ __align__(16) double gemm_smem[];
+
+// Plain C = A B^T (measurement + tests).  grid (N/128, M/128).
+__global__ void __launch_bounds__(CGP_GEMM_THREADS, 1)
+k_dgemm_nt(const double* __restrict__ A, const double* __restrict__ B, double* __restrict__ C, long long M,
+           long long N, int K) {
+    GemmAcc acc;
+    gemm_zero(acc);
+    const double* gA = A + (long long)blockIdx.y * CGP_TILE * K;
+    const double* gB = B + (long long)blockIdx.x * CGP_TILE * K;
+    gemm_mainloop(acc, gemm_smem, gA, K, gB, K, K);
+    gemm_store<0>(acc, C + (long long)blockIdx.y * CGP_TILE * N + (long long)blockIdx.x * CGP_TILE, N);
+}
+
+// Left-looking Cholesky, block column j (j >= 1):  A[i,j] -= sum_{k<j} L[i,k] L[j,k]^T  for i >= j.
+// grid (Tmax - j, n_mats)
+__global__ void __launch_bounds__(CGP_GEMM_THREADS, 1)
+k_potrf_update(double* __restrict__ Abuf, const MatMeta* __restrict__ meta, int j) {
+    const MatMeta m = meta[blockIdx.y];
+    const int T = m.npad / CGP_TILE;
+    const int i = j + blockIdx.x;
+    if (i >= T) return;
+    double* A = Abuf + m.a_off;
+    const long long ld = m.npad;
+    GemmAcc acc;
+    gemm_zero(acc);
+    gemm_mainloop(acc, gemm_smem, A + (long long)i * CGP_TILE * ld, ld, A + (long long)j * CGP_TILE * ld, ld, j * CGP_TILE);
+    gemm_store<2>(acc, A + (long long)i * CGP_TILE * ld + (long long)j * CGP_TILE, ld);
+}
+
+// Panel: L[i,j] = A[i,j] * inv(L[j,j])^T for i > j  (triangular solve recast as a GEMM with the
+// explicitly inverted 128x128 diagonal block D_j, row-major in Dbuf).  grid (Tmax - j - 1, n_mats)
+__global__ void __launch_bounds__(CGP_GEMM_THREADS, 1)
+k_potrf_panel(double* __restrict__ Abuf, const double* __restrict__ Dbuf, const MatMeta* __restrict__ meta, int j) {
+    const MatMeta m = meta[blockIdx.y];
+    const int T = m.npad / CGP_TILE;
+    const int i = j + 1 + blockIdx.x;
+    if (i >= T) return;
+    const long long ld = m.npad;
+    double* tile = Abuf + m.a_off + (long long)i * CGP_TILE * ld + (long long)j * CGP_TILE;
+    const double* D = Dbuf + m.d_off + (long long)j * CGP_TILE * CGP_TILE;
+    GemmAcc acc;
+    gemm_zero(acc);
+    gemm_mainloop(acc, gemm_smem, tile, ld, D, CGP_TILE, CGP_TILE);
+    gemm_store<0>(acc, tile, ld);
+}
+
+// Triangular inverse, stored transposed: U = L^-T (upper, row-major).  Block column i (i >= 1):
+//   S[j,i] = sum_{k=j}^{i-1} U[j,k] L[i,k]^T   for j < i        (this kernel, written to U[j,i])
+//   U[j,i] = -S[j,i] * D_i^T                                     (k_trtri_scale)
+// grid (i, n_mats); heavy tiles (small j) first.
+__global__ void __launch_bounds__(CGP_GEMM_THREADS, 1)
+k_trtri_acc(const double* __restrict__ Abuf, double* __restrict__ Ubuf, const MatMeta* __restrict__ meta, int i) {
+    const MatMeta m = meta[blockIdx.y];
+    const int T = m.npad / CGP_TILE;
+    const int j = blockIdx.x;
+    if (i >= T || j >= i) return;
+    const long long ld = m.npad;
+    const double* L = Abuf + m.a_off;
+    double* U = Ubuf + m.u_off;
+    GemmAcc acc;
+    gemm_zero(acc);
+    gemm_mainloop(acc, gemm_smem, U + (long long)j * CGP_TILE * ld + (long long)j * CGP_TILE, ld,
+                  L + (long long)i * CGP_TILE * ld + (long long)j * CGP_TILE, ld, (i - j) * CGP_TILE);
+    gemm_store<0>(acc, U + (long long)j * CGP_TILE * ld + (long long)i * CGP_TILE, ld);
+}
+
+__global__ void __launch_bounds__(CGP_GEMM_THREADS, 1)
+k_trtri_scale(double* __restrict__ Ubuf, const double* __restrict__ Dbuf, const MatMeta* __restrict__ meta, int i) {
+    const MatMeta m = meta[blockIdx.y];
+    const int T = m.npad / CGP_TILE;
+    const int j = blockIdx.x;
+    if (i >= T || j >= i) return;
+    const long long ld = m.npad;
+    double* tile = Ubuf + m.u_off + (long long)j * CGP_TILE * ld + (long long)i * CGP_TILE;
+    const double* D = Dbuf + m.d_off + (long long)i * CGP_TILE * CGP_TILE;
+    GemmAcc acc;
+    gemm_zero(acc);
+    gemm_mainloop(acc, gemm_smem, tile, ld, D, CGP_TILE, CGP_TILE);
+    gemm_store<1>(acc, tile, ld);
+}
+
+// K^-1 = U U^T, lower tiles (i >= j):  Kinv[i,j] = sum_{k>=i} U[i,k] U[j,k]^T, written over A.
+// grid (Tmax(Tmax+1)/2, n_mats); tiles enumerated i-major so the longest K (i = 0) starts first.
+__global__ void __launch_bounds__(CGP_GEMM_THREADS, 1)
+k_lauum(double* __restrict__ Abuf, const double* __restrict__ Ubuf, const MatMeta* __restrict__ meta) {
+    const MatMeta m = meta[blockIdx.y];
+    const int T = m.npad / CGP_TILE;
+    int idx = blockIdx.x, i = 0;
+    while (idx > i) {
+        idx -= i + 1;
+        ++i;
+    }
+    const int j = idx;
+    if (i >= T) return;
+    const long long ld = m.npad;
+    const double* U = Ubuf + m.u_off;
+    GemmAcc acc;
+    gemm_zero(acc);
+    gemm_mainloop(acc, gemm_smem, U + (long long)i * CGP_TILE * ld + (long long)i * CGP_TILE, ld,
+                  U + (long long)j * CGP_TILE * ld + (long long)i * CGP_TILE, ld, (T - i) * CGP_TILE);
+    gemm_store<0>(acc, Abuf + m.a_off + (long long)i * CGP_TILE * ld + (long long)j * CGP_TILE, ld);
+}
+
+// Predictive variance contraction for one cluster and one candidate chunk:
+//   V[ib-block rows, cand tile] = sum_{k <= ib} W[ib, k] Kstar[cand, k]^T ;  vpart[ib][cand] = sum_rows V^2
+// grid (n_cand_tiles * T); row blocks with the longest K first inside each candidate tile so that
+// consecutive CTAs reuse the same Kstar tile from L2.
+__global__ void __launch_bounds__(CGP_GEMM_THREADS, 1)
+k_predict_vnorm(const double* __restrict__ W, const double* __restrict__ Kstar, double* __restrict__ vpart, int npad,
+                long long cand_stride /* rows in vpart */) {
+    const int T = npad / CGP_TILE;
+    const int ct = blockIdx.x / T;
+    const int ib = T - 1 - (blockIdx.x % T);
+    GemmAcc acc;
+    gemm_zero(acc);
+    gemm_mainloop(acc, gemm_smem, W + (long long)ib * CGP_TILE * npad, npad, Kstar + (long long)ct * CGP_TILE * npad, npad,
+                  (ib + 1) * CGP_TILE);
+    gemm_colsumsq(acc, gemm_smem, vpart + (long long)ib * cand_stride + (long long)ct * CGP_TILE);
+}

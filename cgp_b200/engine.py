@@ -1,0 +1,261 @@
+"""Host-side engine of the per-cluster GP hot path (everything after clustering in one cGP iteration,
+REF/cGP/cGP_constrained.py:287-379): batched fit of all clusters x restarts, k-NN routing, routed
+prediction and the EI candidate scan.  All arithmetic runs in the CUDA extension (cgp_b200/_lib.py);
+this module only moves tensors, drives SciPy's L-BFGS-B state machines in lock-step and shards work
+over ranks.  No CPU fallback.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+
+from . import _lib, dist as cdist
+from .lbfgs import minimize_lockstep
+
+LOG_LO = math.log(1e-5)  # REF/cGP/cGP_constrained.py:169
+LOG_HI = math.log(1e5)
+
+
+def restart_thetas(P, R, seed=0, lo=None, hi=None):
+    """Start points of runs 0..R (SK/gaussian_process/_gpr.py:312-333): run 0 = kernel theta (0 for the
+    reference's template), runs 1..R = RandomState(seed).uniform(lo, hi) drawn sequentially.  The draws do
+    not depend on results, so they are pre-drawn and shared by every cluster (random_state=0 per fit,
+    REF/cGP/cGP_constrained.py:315)."""
+    rng = np.random.RandomState(seed)
+    lo = np.full(P, LOG_LO) if lo is None else np.asarray(lo, float)
+    hi = np.full(P, LOG_HI) if hi is None else np.asarray(hi, float)
+    out = np.zeros((R + 1, P))
+    for r in range(R):
+        out[r + 1] = rng.uniform(lo, hi)
+    return out
+
+
+class ClusterGPEngine:
+    """Device-resident state of one clustered GP surrogate."""
+
+    def __init__(self, X, y, labels, kind="matern32", alpha=1e-5, normalize_y=True, device=None,
+                 mem_fraction=0.6):
+        if not torch.cuda.is_available():
+            raise _lib.CgpError("cgp_b200 needs a CUDA device (B200); there is no CPU fallback")
+        _lib.lib()
+        self.device = torch.device("cuda", torch.cuda.current_device() if device is None else device)
+        X = np.ascontiguousarray(np.asarray(X, dtype=np.float64))
+        y = np.asarray(y, dtype=np.float64).reshape(-1)
+        labels = np.asarray(labels).astype(np.int64).reshape(-1)
+        if X.ndim != 2 or X.shape[0] != y.shape[0] or labels.shape[0] != y.shape[0]:
+            raise ValueError("X [n,d], y [n], labels [n] expected")
+        self.kind = kind
+        self.alpha = float(alpha)
+        self.n, self.d = X.shape
+        self.P = self.d + 1
+        self.C = int(labels.max()) + 1
+        counts = np.bincount(labels, minlength=self.C)
+        if np.any(counts == 0) or labels.min() < 0:
+            raise ValueError("labels must be recoded to 0..C-1 with no empty cluster "
+                             "(REF/cGP/cGP_constrained.py:249-255)")
+        self.order = np.argsort(labels, kind="stable")  # cluster-sorted row order
+        self.offs = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+        self.counts = counts
+        Xs = X[self.order]
+        ys = y[self.order]
+        # per-cluster target normalisation on the host, exactly as SK/_gpr.py:275-280
+        self.y_mean = np.zeros(self.C)
+        self.y_std = np.ones(self.C)
+        self.y_max = np.zeros(self.C)
+        yn = np.empty_like(ys)
+        for c in range(self.C):
+            seg = ys[self.offs[c]:self.offs[c + 1]]
+            self.y_max[c] = np.max(seg)  # incumbent of REF/cGP/acquisition.py:23
+            if normalize_y:
+                m = np.mean(seg)
+                s = np.std(seg)
+                if s < 10 * np.finfo(np.float64).eps:  # _handle_zeros_in_scale
+                    s = 1.0
+                self.y_mean[c], self.y_std[c] = m, s
+            yn[self.offs[c]:self.offs[c + 1]] = (seg - self.y_mean[c]) / self.y_std[c]
+        dev = self.device
+        self.X_host, self.y_host, self.labels_host = X, y, labels
+        self.Xs = torch.from_numpy(Xs).to(dev)
+        self.yn = torch.from_numpy(yn).to(dev)
+        self.yn_host = yn
+        self.X_orig = torch.from_numpy(X).to(dev)
+        self.labels_dev = torch.from_numpy(labels).to(dev)
+        self.y_mean_dev = torch.from_numpy(self.y_mean).to(dev)
+        self.y_std_dev = torch.from_numpy(self.y_std).to(dev)
+        self.y_max_dev = torch.from_numpy(self.y_max).to(dev)
+        self.mem_fraction = mem_fraction
+        self.theta = None
+        self.model = None
+        self._ws = None
+        self.fit_stats = {}
+
+    # ------------------------------------------------------------------ workspace
+    def _workspace(self, nbytes):
+        free, _total = torch.cuda.mem_get_info(self.device)
+        have = 0 if self._ws is None else self._ws.numel()
+        if have >= nbytes:
+            return self._ws
+        budget = int((free + have) * self.mem_fraction)
+        want = min(nbytes, budget)
+        if want > have:
+            self._ws = None
+            self._ws = torch.empty(want, dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    # ------------------------------------------------------------------ LML
+    def lml_grad(self, pair_cluster, thetas, want_grad=True):
+        """Batched log-marginal likelihood (+ gradient) for pairs (cluster, theta).  Host arrays in/out.
+        Non-PD -> (-inf, 0) as SK/_gpr.py:592-593."""
+        pair_cluster = np.asarray(pair_cluster, dtype=np.int32)
+        thetas = np.ascontiguousarray(np.asarray(thetas, dtype=np.float64).reshape(len(pair_cluster), self.P))
+        need = _lib.lml_workspace_bytes(self.offs, pair_cluster, self.d)
+        ws = self._workspace(need)
+        th = torch.from_numpy(thetas).to(self.device)
+        lml, grad, info = _lib.lml_grad_batched(self.Xs, self.yn, self.offs, pair_cluster, th, self.alpha, self.kind,
+                                                ws, want_grad)
+        lml = lml.cpu().numpy()
+        info = info.cpu().numpy()
+        bad = info != 0
+        lml[bad] = -np.inf
+        if want_grad:
+            grad = grad.cpu().numpy()
+            grad[bad] = 0.0
+            return lml, grad, info
+        return lml, None, info
+
+    # ------------------------------------------------------------------ fit
+    def fit(self, n_restarts, seed=0, theta0=None, bounds=None, optimize=True):
+        """All clusters x (R+1) restarts in lock-step (SK/_gpr.py:296-340), sharded round-robin over ranks,
+        then the final factorisation at each cluster's best theta (SK/_gpr.py:349-367)."""
+        rank, ws = cdist.world()
+        P, C = self.P, self.C
+        lo = np.full(P, LOG_LO) if bounds is None else np.asarray(bounds, float)[:, 0]
+        hi = np.full(P, LOG_HI) if bounds is None else np.asarray(bounds, float)[:, 1]
+        starts = restart_thetas(P, n_restarts, seed, lo, hi)
+        if theta0 is not None:
+            starts[0] = np.asarray(theta0, float)
+        R1 = starts.shape[0]
+        if not optimize:
+            self.theta = np.tile(starts[0], (C, 1))
+            self._factorize()
+            return self
+        n_pairs = C * R1  # pair p = (cluster p // R1, run p % R1)
+        mine = cdist.my_pairs(n_pairs, rank, ws)
+        pc_all = np.asarray([p // R1 for p in mine], dtype=np.int32)
+        x0s = [starts[p % R1] for p in mine]
+        n_eval = [0]
+
+        def eval_batch(idx, Xs):
+            lml, grad, _ = self.lml_grad(pc_all[idx], Xs, True)
+            n_eval[0] += len(idx)
+            return -lml, -grad
+
+        xs, fs, nfev, nit, steps = minimize_lockstep(eval_batch, x0s, lo, hi)
+        rows = torch.from_numpy(np.concatenate([xs, fs[:, None]], axis=1).reshape(len(mine), P + 1)).to(self.device)
+        table = cdist.gather_pair_rows(rows, n_pairs, rank, ws).cpu().numpy().reshape(C, R1, P + 1)
+        self.run_thetas = table[:, :, :P]
+        self.run_values = table[:, :, P]
+        best = np.argmin(self.run_values, axis=1)  # first minimum in run order, SK/_gpr.py:336-337
+        self.theta = np.stack([self.run_thetas[c, best[c]] for c in range(C)])
+        self.fit_stats = dict(lockstep=steps, evals=int(n_eval[0]), nfev=nfev, nit=nit, pairs_local=len(mine),
+                              pairs_total=n_pairs)
+        self._factorize()
+        return self
+
+    def set_theta(self, theta):
+        self.theta = np.asarray(theta, dtype=np.float64).reshape(self.C, self.P).copy()
+        self._factorize()
+        return self
+
+    def _factorize(self):
+        th = torch.from_numpy(np.ascontiguousarray(self.theta)).to(self.device)
+        need = _lib.factorize_workspace_bytes(self.offs, self.d)
+        ws = self._workspace(need)
+        if ws.numel() < need:
+            raise _lib.CgpError("not enough device memory for the final factorisation")
+        m = _lib.factorize(self.Xs, self.yn, self.offs, th, self.alpha, self.kind, ws)
+        info = m["info"].cpu().numpy()
+        if np.any(info != 0):
+            c = int(np.nonzero(info)[0][0])
+            raise np.linalg.LinAlgError(
+                f"The kernel of cluster {c} is not returning a positive definite matrix "
+                f"({info[c]}-th leading minor). Try gradually increasing the 'alpha' parameter "
+                "of your GaussianProcessRegressor estimator.")  # SK/_gpr.py:353-361
+        m["theta_dev"] = th
+        m["lml_host"] = m["lml"].cpu().numpy()
+        self.model = m
+        npad = [_lib.padded_n(int(c)) for c in self.counts]
+        self.npad = np.asarray(npad, dtype=np.int64)
+        self.moff = np.concatenate([[0], np.cumsum(self.npad * self.npad)]).astype(np.int64)
+
+    # ------------------------------------------------------------------ accessors (host copies)
+    def L_of(self, c):
+        npd, n = int(self.npad[c]), int(self.counts[c])
+        return self.model["L"][self.moff[c]:self.moff[c + 1]].view(npd, npd)[:n, :n].cpu().numpy()
+
+    def W_of(self, c):
+        npd, n = int(self.npad[c]), int(self.counts[c])
+        return self.model["W"][self.moff[c]:self.moff[c + 1]].view(npd, npd)[:n, :n].cpu().numpy()
+
+    def alpha_of(self, c):
+        return self.model["alpha_vec"][self.offs[c]:self.offs[c + 1]].cpu().numpy()
+
+    # ------------------------------------------------------------------ routing / prediction / acquisition
+    def _to_dev(self, Q):
+        if isinstance(Q, torch.Tensor):
+            return Q.to(self.device, torch.float64).contiguous()
+        return torch.from_numpy(np.ascontiguousarray(np.asarray(Q, dtype=np.float64))).to(self.device)
+
+    def route(self, Q, k=3):
+        """k-NN cluster labels of Q (REF/cGP/acquisition.py:7)."""
+        Qd = self._to_dev(Q)
+        return _lib.knn_labels(self.X_orig, self.labels_dev, Qd, min(k, self.n), self.C)
+
+    def predict(self, Q, qlabel=None, k=3, return_std=True):
+        """Routed posterior mean/std (REF/cGP/f_truth_dill.py:20-30)."""
+        Qd = self._to_dev(Q)
+        if qlabel is None:
+            qlabel = self.route(Qd, k)
+        m = self.model
+        ws = self._workspace(_lib.score_workspace_bytes(self.offs, self.d, Qd.shape[0]))
+        return _lib.predict(self.Xs, self.offs, m["theta_dev"], m["W"], m["alpha_vec"], self.y_mean_dev, self.y_std_dev,
+                            Qd, qlabel, self.kind, return_std, ws)
+
+    def ei_scan(self, Q, k=3, idx_base=0, want_arrays=False, qlabel=None):
+        """Dense EI scan of candidates Q -> ((score, idx, cluster) CUDA 1-elem tensors, arrays)."""
+        Qd = self._to_dev(Q)
+        if qlabel is None:
+            qlabel = self.route(Qd, k)
+        m = self.model
+        ws = self._workspace(_lib.score_workspace_bytes(self.offs, self.d, Qd.shape[0]))
+        return _lib.ei_argmax(self.Xs, self.offs, m["theta_dev"], m["W"], m["alpha_vec"], self.y_mean_dev,
+                              self.y_std_dev, self.y_max_dev, Qd, qlabel, self.kind, idx_base, want_arrays, ws)
+
+    def select_next(self, candidates, k=3, sharded=False):
+        """Pick the next sample from `candidates` [M,d].
+
+        sharded=False: `candidates` is the full array (identical on every rank); each rank scores its
+        contiguous shard.  sharded=True: `candidates` is already this rank's shard and idx_base is derived
+        from the shard sizes (all-gathered).  Returns (x_next np[d], score, global idx, cluster)."""
+        rank, ws = cdist.world()
+        if sharded:
+            local = self._to_dev(candidates)
+            sizes = torch.tensor([local.shape[0]], dtype=torch.int64, device=self.device)
+            if ws > 1:
+                alls = torch.empty(ws, dtype=torch.int64, device=self.device)
+                torch.distributed.all_gather_into_tensor(alls, sizes)
+                base = int(alls[:rank].sum().item())
+            else:
+                base = 0
+        else:
+            M = candidates.shape[0]
+            lo, hi = cdist.shard_range(M, rank, ws)
+            local = self._to_dev(candidates[lo:hi])
+            base = lo
+        (bs, bi, bc), _ = self.ei_scan(local, k, idx_base=base)
+        li = int(bi.item()) - base
+        x_local = local[li] if li >= 0 else torch.zeros(self.d, dtype=torch.float64, device=self.device)
+        score, idx, cl, x, _owner = cdist.reduce_best(bs, bi, bc, x_local, rank, ws)
+        return x.cpu().numpy(), score, idx, cl

@@ -1,0 +1,98 @@
+"""Lock-step L-BFGS-B over many independent (cluster, restart) problems.
+
+The optimiser arithmetic stays on the host and is SciPy's own reverse-communication routine
+``_lbfgsb.setulb`` driven exactly like ``scipy.optimize._lbfgsb_py._minimize_lbfgsb`` (SP/optimize/
+_lbfgsb_py.py:272-461: m=10, factr=ftol/eps with ftol=2.22e-9, pgtol=1e-5, maxls=20, maxiter=maxfun=15000),
+which is what ``GaussianProcessRegressor._constrained_optimization`` calls (SK/gaussian_process/_gpr.py:658-674).
+Instead of one objective call per run, every run that is waiting for (f, g) is evaluated in ONE batched GPU
+launch per lock-step.
+"""
+from __future__ import annotations
+
+import numpy as np
+from scipy.linalg.lapack import HAS_ILP64
+from scipy.optimize import _lbfgsb
+
+_INT = np.int64 if HAS_ILP64 else np.int32
+
+
+class _Run:
+    """One L-BFGS-B state machine (the body of _minimize_lbfgsb's while-loop, turned inside out)."""
+
+    __slots__ = ("x", "f", "g", "lo", "hi", "nbd", "wa", "iwa", "task", "ln_task", "lsave", "isave", "dsave", "m",
+                 "factr", "pgtol", "maxls", "maxiter", "maxfun", "nit", "nfev", "done")
+
+    def __init__(self, x0, lo, hi, m=10, ftol=2.2204460492503131e-09, gtol=1e-5, maxfun=15000, maxiter=15000,
+                 maxls=20):
+        n = x0.shape[0]
+        self.lo = np.array(lo, dtype=np.float64)
+        self.hi = np.array(hi, dtype=np.float64)
+        self.x = np.clip(np.array(x0, dtype=np.float64), self.lo, self.hi)  # _lbfgsb_py.py:360
+        self.nbd = np.full(n, 2, dtype=_INT)  # both bounds finite
+        self.f = np.array(0.0, dtype=np.float64)
+        self.g = np.zeros(n, dtype=np.float64)
+        self.m = m
+        self.factr = ftol / np.finfo(float).eps
+        self.pgtol = gtol
+        self.maxls = maxls
+        self.maxiter = maxiter
+        self.maxfun = maxfun
+        self.wa = np.zeros(2 * m * n + 5 * n + 11 * m * m + 8 * m, np.float64)
+        self.iwa = np.zeros(3 * n, dtype=_INT)
+        self.task = np.zeros(2, dtype=_INT)
+        self.ln_task = np.zeros(2, dtype=_INT)
+        self.lsave = np.zeros(4, dtype=_INT)
+        self.isave = np.zeros(44, dtype=_INT)
+        self.dsave = np.zeros(29, dtype=np.float64)
+        self.nit = 0
+        self.nfev = 0
+        self.done = False
+
+    def advance(self):
+        """Run setulb until it asks for (f, g) at self.x (returns True) or terminates (returns False)."""
+        while True:
+            self.g = self.g.astype(np.float64)
+            _lbfgsb.setulb(self.m, self.x, self.lo, self.hi, self.nbd, self.f, self.g, self.factr, self.pgtol, self.wa,
+                           self.iwa, self.task, self.lsave, self.isave, self.dsave, self.maxls, self.ln_task)
+            if self.task[0] == 3:
+                return True
+            if self.task[0] == 1:
+                self.nit += 1
+                if self.nit >= self.maxiter:
+                    self.task[0] = 5
+                    self.task[1] = 504
+                elif self.nfev > self.maxfun:
+                    self.task[0] = 5
+                    self.task[1] = 502
+            else:
+                self.done = True
+                return False
+
+    def feed(self, f, g):
+        self.f = float(f)
+        self.g = np.array(g, dtype=np.float64)
+        self.nfev += 1
+
+
+def minimize_lockstep(eval_batch, x0s, lo, hi, max_steps=100000):
+    """Minimise len(x0s) independent problems.
+
+    eval_batch(idx: int array [b], X: float array [b, n]) -> (f [b], g [b, n]) evaluates problems `idx` at `X`.
+    Returns (x [R, n], f [R], nfev [R], nit [R], n_lockstep)."""
+    runs = [_Run(np.asarray(x0), lo, hi) for x0 in x0s]
+    waiting = [i for i, r in enumerate(runs) if r.advance()]
+    steps = 0
+    while waiting and steps < max_steps:
+        idx = np.asarray(waiting, dtype=np.int64)
+        X = np.stack([runs[i].x.copy() for i in waiting])
+        f, g = eval_batch(idx, X)
+        nxt = []
+        for k, i in enumerate(waiting):
+            runs[i].feed(f[k], g[k])
+            if runs[i].advance():
+                nxt.append(i)
+        waiting = nxt
+        steps += 1
+    xs = np.stack([r.x for r in runs])
+    fs = np.array([float(r.f) for r in runs])
+    return xs, fs, np.array([r.nfev for r in runs]), np.array([r.nit for r in runs]), steps

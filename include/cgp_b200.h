@@ -1,0 +1,131 @@
+/*
+ * cgp_b200 — C-ABI of the B200-native per-cluster GP hot path of gptune/cGP.
+ *
+ * The reference (pure Python) has no FFI: the boundary it crosses for this path is the
+ * scikit-learn object API.  Each entry point below replaces the reference call site cited
+ * beside it (REF = /root/reference, SK = scikit-learn 1.9.0, SP = SciPy 1.18.1); the Python
+ * binding a maintainer would add is cgp_b200/_lib.py (ctypes) — see INTEGRATION.md.
+ *
+ * Conventions
+ *   - all bulk pointers are DEVICE pointers to contiguous fp64 / int64 arrays owned by the caller;
+ *     pointers named *_host are small HOST arrays (launch geometry);
+ *   - `stream` is a cudaStream_t passed as void*; every call is asynchronous on it;
+ *   - the library never allocates device memory: callers pass a workspace sized by the
+ *     matching *_workspace_bytes() query;
+ *   - return value: 0 OK; <0 argument -i invalid (LAPACK style); >0 cudaError_t.
+ *     Numerical status is per item in `info[]`: 0 OK, j>0 leading minor j not positive definite
+ *     (LAPACK dpotrf convention; SK/gaussian_process/_gpr.py:591-593 maps it to lml=-inf, grad=0).
+ *   - training rows are stored CLUSTER-SORTED: cluster c owns rows offs[c]..offs[c+1]-1 of X / y
+ *     (REF/cGP/cGP_constrained.py:307-312 slices them per cluster).
+ *   - theta = [log l_1..log l_d, log sigma_n^2]  (SK/gaussian_process/kernels.py:752,763-765),
+ *     P = d + 1.
+ *   - factor storage: every cluster matrix is padded to npad = cgp_padded_n(n_c) (multiple of the
+ *     128-wide tile) and stored row-major [npad, npad]; cluster c starts at element
+ *     sum_{c'<c} npad_{c'}^2.  The pad block is the identity.
+ */
+#ifndef CGP_B200_H
+#define CGP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct cgp_handle cgp_handle;
+
+enum { CGP_KIND_MATERN32 = 0, CGP_KIND_RBF = 1 };
+
+/* Library version (major*10000 + minor*100 + patch). */
+int cgp_version(void);
+
+/* Handle: device id, SM count and a small pinned staging buffer for launch metadata. */
+int cgp_create(cgp_handle** out, int device);
+int cgp_destroy(cgp_handle* h);
+
+/* npad for a cluster of n samples. */
+int64_t cgp_padded_n(int64_t n);
+/* sum_c npad_c^2 — element count of the L / W factor buffers. */
+int64_t cgp_model_elems(const int64_t* offs_host, int n_clusters);
+
+/* K1: dense kernel matrix K = k(X,X) + (exp(theta[d]) + alpha) I, row-major [n,n].
+ * Replaces `kernel_(X_train_)` + `K[diag] += alpha`, SK/gaussian_process/_gpr.py:584-589,349-350
+ * (Matern nu=1.5: SK kernels.py:1713-1743; RBF :1558-1565; White :1406-1407; Sum :866-871). */
+int cgp_kernel_matrix(cgp_handle* h, int kind, const double* X, int64_t n, int d,
+                      const double* theta, double alpha, double* K, void* stream);
+
+/* Cross kernel k(Q, X) [m,n] (White contributes 0, SK kernels.py:1418-1419);
+ * replaces `kernel_(X, X_train_)`, SK/_gpr.py:447. */
+int cgp_kernel_cross(cgp_handle* h, int kind, const double* Q, int64_t m, const double* X, int64_t n,
+                     int d, const double* theta, double* Kqx, void* stream);
+
+/* K2..K6: log-marginal likelihood and gradient for B (cluster, theta) pairs in one call.
+ * Replaces `GaussianProcessRegressor.log_marginal_likelihood(theta, eval_gradient=True)`,
+ * SK/_gpr.py:541-656, called once per L-BFGS-B evaluation per restart per cluster
+ * (SK/_gpr.py:302-333; REF/cGP/cGP_constrained.py:327).
+ *   y          normalised targets (SK/_gpr.py:275-280), cluster-sorted
+ *   pair_cluster_host[B]  cluster of each pair;  theta [B,P] device
+ *   lml[B], grad[B,P] (grad may be NULL), info[B] device outputs. */
+size_t cgp_lml_workspace_bytes(const int64_t* offs_host, int n_clusters,
+                               const int32_t* pair_cluster_host, int n_pairs, int d);
+int cgp_lml_grad_batched(cgp_handle* h, int kind, const double* X, const double* y,
+                         const int64_t* offs_host, int n_clusters, int d,
+                         const int32_t* pair_cluster_host, int n_pairs, const double* theta,
+                         double alpha, double* lml, double* grad, int32_t* info,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
+/* Final factorisation at the selected theta of every cluster.
+ * Replaces SK/_gpr.py:349-367 (`L_ = cholesky(K)`, `alpha_ = cho_solve(L_, y)`).
+ *   L [model_elems]   lower Cholesky factors (padded layout)
+ *   W [model_elems]   W = L^-1 (lower) — what the predict kernel multiplies by instead of
+ *                     LAPACK dtrtrs (SK/_gpr.py:460)
+ *   alpha_vec [n]     K^-1 y, cluster-sorted;  lml[C];  info[C]. */
+size_t cgp_factorize_workspace_bytes(const int64_t* offs_host, int n_clusters, int d);
+int cgp_factorize(cgp_handle* h, int kind, const double* X, const double* y,
+                  const int64_t* offs_host, int n_clusters, int d, const double* theta,
+                  double alpha, double* L, double* W, double* alpha_vec, double* lml,
+                  int32_t* info, void* workspace, size_t workspace_bytes, void* stream);
+
+/* K7: k-NN routing.  Replaces `classify.predict(X)`, REF/cGP/acquisition.py:7 ->
+ * SK/neighbors/_classification.py:245-312 (k nearest by exact fp64 squared Euclidean distance,
+ * un-fused mul/add as SK/metrics/_dist_metrics.pxd.tp:44-49; distance ties -> lowest training
+ * index; vote ties -> smallest label).  X here is in the ORIGINAL sample order with labels[n]. */
+int cgp_knn_labels(cgp_handle* h, const double* X, const int64_t* labels, int64_t n, int d, int k,
+                   int n_classes, const double* Q, int64_t m, int64_t* out_labels, void* stream);
+
+/* K8: routed posterior mean / std for m query points.
+ * Replaces `GPR_list[label].predict(x, return_std=True)`, REF/cGP/f_truth_dill.py:20-30 and
+ * SK/_gpr.py:446-500.  X / alpha_vec cluster-sorted, theta [C,P], y_mean[C], y_std[C] device.
+ * mean[m], std[m] in the caller's query order (std may be NULL). */
+size_t cgp_score_workspace_bytes(const int64_t* offs_host, int n_clusters, int d, int64_t m);
+int cgp_predict(cgp_handle* h, int kind, const double* X, const int64_t* offs_host, int n_clusters,
+                int d, const double* theta, const double* W, const double* alpha_vec,
+                const double* y_mean, const double* y_std, const double* Q,
+                const int64_t* qlabel, int64_t m, double* mean, double* std,
+                void* workspace, size_t workspace_bytes, void* stream);
+
+/* K8 + EI + argmax.  Replaces the per-point `expected_improvement` objective,
+ * REF/cGP/acquisition.py:4-32, and the cross-cluster strict-max, REF/cGP/cGP_constrained.py:376-378,
+ * by a dense scan of m candidates:
+ *   score_i = EI(mean_i, std_i; y_max[c]) / n_c   with c = qlabel[i]
+ *   best = argmax score; ties -> lowest cluster id, then lowest candidate index.
+ * Outputs (device): best_score[1], best_idx[1] (index into Q, plus idx_base), best_cluster[1];
+ * score/mean/std [m] optional (NULL to skip). */
+int cgp_ei_argmax(cgp_handle* h, int kind, const double* X, const int64_t* offs_host,
+                  int n_clusters, int d, const double* theta, const double* W,
+                  const double* alpha_vec, const double* y_mean, const double* y_std,
+                  const double* y_max, const double* Q, const int64_t* qlabel, int64_t m,
+                  int64_t idx_base, double* score, double* mean, double* std, double* best_score,
+                  int64_t* best_idx, int64_t* best_cluster, void* workspace,
+                  size_t workspace_bytes, void* stream);
+
+/* Measurement helper (bench / tests only): C[M,N] = A[M,K] * B[N,K]^T through the same fp64
+ * tensor-core (DMMA) tile mainloop every factorisation step uses.  M,N multiples of 128, K of 16. */
+int cgp_dgemm_nt(cgp_handle* h, const double* A, const double* B, double* C, int64_t M, int64_t N,
+                 int64_t K, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CGP_B200_H */

@@ -1,0 +1,72 @@
+"""CPU, world_size 2 over gloo: the multi-GPU plumbing (pair dealing, theta* all-gather, EI-maxima all-gather with the
+reference's tie rule, broadcast of the selected point) gives the same answer as a single rank."""
+import os
+import socket
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from cgp_b200 import dist as cdist
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        # ---- fit exchange: 3 clusters x 5 runs, P = 4
+        n_pairs, P = 15, 4
+        rng = np.random.default_rng(0)
+        table = rng.normal(size=(n_pairs, P + 1))
+        mine = cdist.my_pairs(n_pairs, rank, world)
+        full = cdist.gather_pair_rows(torch.from_numpy(table[mine]), n_pairs, rank, world)
+        ok_fit = bool(np.array_equal(full.numpy(), table))
+        # ---- scoring exchange: 1001 candidates, scores with an exact tie across the two shards
+        M, d = 1001, 3
+        Q = rng.uniform(size=(M, d))
+        score = rng.uniform(size=M)
+        cluster = rng.integers(0, 4, size=M)
+        score[[100, 900]] = 2.0  # tie: lower cluster id wins, then lower index
+        cluster[100], cluster[900] = 3, 1
+        lo, hi = cdist.shard_range(M, rank, world)
+        j = lo + int(np.argmax(score[lo:hi]))
+        s, i, c, x, owner = cdist.reduce_best(torch.tensor([score[j]]), torch.tensor([j]), torch.tensor([cluster[j]]),
+                                              torch.from_numpy(Q[j].copy()), rank, world)
+        ok_sel = (i == 900 and c == 1 and s == 2.0 and np.array_equal(x.numpy(), Q[900]) and owner == 1)
+        q.put((rank, ok_fit, ok_sel, (lo, hi)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_world2_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res[0][3] == (0, 500) and res[1][3] == (500, 1001)
+    for rank, ok_fit, ok_sel, _ in res:
+        assert ok_fit and ok_sel, (rank, ok_fit, ok_sel)
+
+
+def test_single_rank_passthrough():
+    assert cdist.world() == (0, 1)
+    assert cdist.shard_range(10, 0, 1) == (0, 10)
+    assert cdist.my_pairs(5, 1, 2) == [1, 3]
+    t = torch.arange(6.0).reshape(2, 3)
+    assert cdist.gather_pair_rows(t, 2, 0, 1) is t

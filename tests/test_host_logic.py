@@ -1,0 +1,88 @@
+"""CPU: host-side logic — lock-step L-BFGS-B equals scipy.optimize.minimize bit for bit, restart draws equal
+scikit-learn's, kernel parsing, plugin contracts."""
+import numpy as np
+import scipy.optimize
+
+import oracle
+from cgp_b200.engine import LOG_HI, LOG_LO, restart_thetas
+from cgp_b200.lbfgs import minimize_lockstep
+
+
+def test_lockstep_equals_scipy():
+    rng = np.random.default_rng(0)
+    X = rng.uniform(size=(60, 3))
+    y, _, _ = oracle.normalize_y(np.sin(4 * X[:, 0]) + X[:, 1] ** 2 + 0.05 * rng.standard_normal(60))
+    starts = restart_thetas(4, 5)
+    lo, hi = np.full(4, LOG_LO), np.full(4, LOG_HI)
+
+    def evalb(idx, Xs):
+        out = [oracle.lml_and_grad(X, y, th) for th in Xs]
+        return np.array([-o[0] for o in out]), np.array([-o[1] for o in out])
+
+    xs, fs, nfev, nit, steps = minimize_lockstep(evalb, starts, lo, hi)
+    for i, t0 in enumerate(starts):
+        res = scipy.optimize.minimize(lambda th: tuple(-v for v in oracle.lml_and_grad(X, y, th)), t0,
+                                      method="L-BFGS-B", jac=True, bounds=list(zip(lo, hi)))
+        assert np.array_equal(res.x, xs[i]) and res.fun == fs[i] and res.nit == nit[i]
+    assert steps == nfev.max()
+
+
+def test_lockstep_handles_inf():
+    """Non-PD evaluations return (+inf, 0) like SK/_gpr.py:592-593; the state machine must terminate."""
+    def evalb(idx, Xs):
+        f = np.where(Xs[:, 0] > 1.0, np.inf, (Xs ** 2).sum(1))
+        g = np.where((Xs[:, 0] > 1.0)[:, None], 0.0, 2 * Xs)
+        return f, g
+
+    xs, fs, *_ = minimize_lockstep(evalb, [np.array([0.9, 0.5]), np.array([2.0, 2.0])], np.full(2, -5.0), np.full(2, 5.0))
+    assert np.all(np.isfinite(xs))
+    assert abs(fs[0]) < 1e-8
+
+
+def test_restart_draws_match_sklearn():
+    from sklearn.utils import check_random_state
+
+    rng = check_random_state(0)
+    b = np.tile([LOG_LO, LOG_HI], (7, 1))
+    want = [rng.uniform(b[:, 0], b[:, 1]) for _ in range(4)]
+    got = restart_thetas(7, 4, 0)
+    assert np.array_equal(got[0], np.zeros(7))
+    assert np.array_equal(got[1:], np.array(want))
+    assert np.array_equal(got, oracle.restart_thetas(7, 4, 0))
+
+
+def test_parse_kernel():
+    from sklearn.gaussian_process.kernels import RBF, Matern, WhiteKernel
+
+    from cgp_b200.gpr import parse_kernel
+
+    k = Matern(length_scale=np.ones(3), length_scale_bounds=(1e-05, 100000.0), nu=3 / 2) + \
+        WhiteKernel(noise_level=1.0, noise_level_bounds=(1e-05, 100000.0))
+    kind, th0, b, tmpl = parse_kernel(k, 3)
+    assert kind == "matern32" and np.array_equal(th0, np.zeros(4)) and tmpl is k
+    assert np.allclose(b, np.tile([LOG_LO, LOG_HI], (4, 1)))
+    kind, *_ = parse_kernel(RBF(np.ones(2), (1e-5, 1e5)) + WhiteKernel(1.0, (1e-5, 1e5)), 2)
+    assert kind == "rbf"
+    import pytest
+
+    with pytest.raises(NotImplementedError):
+        parse_kernel(Matern(np.ones(2), nu=2.5) + WhiteKernel(), 2)
+    with pytest.raises(NotImplementedError):
+        parse_kernel(RBF(np.ones(2)), 2)
+
+
+def test_plugin_contracts():
+    import importlib
+
+    for name, k in [("cluster", 3), ("DGM2", 2), ("DGM5", 5)]:
+        obj = importlib.import_module(f"cgp_b200.plugins.{name}").f_Cluster(123)
+        assert obj.n_components == k and obj.random_state == 123 and hasattr(obj, "fit_predict")
+        assert obj.weight_concentration_prior_type == "dirichlet_process"
+    for k in range(1, 6):
+        obj = importlib.import_module(f"cgp_b200.plugins.KMeans{k}").f_Cluster(7)
+        assert obj.n_clusters == k and obj.random_state == 7
+    clf = importlib.import_module("cgp_b200.plugins.classify").f_Classify()
+    assert clf.n_neighbors == 3 and hasattr(clf, "fit") and hasattr(clf, "predict")
+    XY = np.random.default_rng(0).normal(size=(40, 3))
+    lab = importlib.import_module("cgp_b200.plugins.KMeans2").f_Cluster(0).fit_predict(XY)
+    assert lab.shape == (40,)
