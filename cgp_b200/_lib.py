@@ -42,6 +42,10 @@ SIGNATURES = {
     "cgp_ei_argmax": (C.c_int, [_vp, C.c_int, _vp, _pi64, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                 _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "cgp_dgemm_nt": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp]),
+    "cgp_profile_classes": (C.c_int, []),
+    "cgp_profile_class_name": (C.c_char_p, [C.c_int]),
+    "cgp_profile_enable": (C.c_int, [_vp, C.c_int]),
+    "cgp_profile_read": (C.c_int, [_vp, C.POINTER(C.c_double), _pi64, C.c_int, C.c_int]),
 }
 
 _lib = None
@@ -248,3 +252,18 @@ def ei_argmax(X, offs, theta, W, alpha_vec, y_mean, y_std, y_max, Q, qlabel, kin
                              _ptr(bs), _ptr(bi, torch.int64), _ptr(bc, torch.int64), _ptr(workspace, torch.uint8),
                              workspace.numel(), _stream()), "cgp_ei_argmax")
     return (bs, bi, bc), (score, mean, std)
+
+
+# ------------------------------------------------------------------------------------------------ measurement
+def profile_enable(on=True, device=None):
+    _chk(lib().cgp_profile_enable(handle(device), 1 if on else 0), "cgp_profile_enable")
+
+
+def profile_read(reset=True, device=None):
+    """-> {class name: (milliseconds, launches)} accumulated since the last reset (synchronises)."""
+    L = lib()
+    n = L.cgp_profile_classes()
+    ms = (C.c_double * n)()
+    cnt = (C.c_int64 * n)()
+    _chk(L.cgp_profile_read(handle(device), ms, cnt, n, 1 if reset else 0), "cgp_profile_read")
+    return {L.cgp_profile_class_name(i).decode(): (float(ms[i]), int(cnt[i])) for i in range(n)}

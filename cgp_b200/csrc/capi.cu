@@ -19,10 +19,57 @@
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 static inline int64_t pad_n(int64_t n) { return (n + CGP_TILE - 1) / CGP_TILE * CGP_TILE; }
 
+enum {
+    CLS_ASSEMBLE, CLS_POTRF_UPDATE, CLS_POTRF_DIAG, CLS_POTRF_PANEL, CLS_TRTRI_ACC, CLS_TRTRI_SCALE, CLS_SOLVE,
+    CLS_LAUUM, CLS_GRAD, CLS_TRANSPOSE, CLS_KNN, CLS_BUCKET, CLS_CROSS, CLS_MEAN, CLS_PREDICT_VNORM,
+    CLS_SCORE_FINISH, CLS_ARGMAX, CLS_DGEMM, CLS_COUNT
+};
+static const char* const kClassNames[CLS_COUNT] = {
+    "assemble", "potrf_update", "potrf_diag", "potrf_panel", "trtri_acc", "trtri_scale", "solve_lml",
+    "lauum", "grad", "transpose", "knn", "bucket", "cross", "mean", "predict_vnorm",
+    "score_finish", "argmax", "dgemm_nt"};
+
+struct ProfRec {
+    cudaEvent_t a, b;
+    int cls;
+};
+
 struct HandleImpl : cgp_handle {
     cudaEvent_t ring_event;
     bool ring_event_pending;
+    // per-kernel-class launch counters (always) and CUDA-event timing (when enabled)
+    bool prof_on;
+    std::vector<ProfRec> recs;
+    size_t recs_used;
+    double ms[CLS_COUNT];
+    long long launches[CLS_COUNT];
 };
+
+static inline void prof_begin(HandleImpl* h, int cls, cudaStream_t s) {
+    h->launches[cls]++;
+    if (!h->prof_on) return;
+    if (h->recs_used == h->recs.size()) {
+        ProfRec r;
+        cudaEventCreate(&r.a);
+        cudaEventCreate(&r.b);
+        h->recs.push_back(r);
+    }
+    ProfRec& r = h->recs[h->recs_used];
+    r.cls = cls;
+    cudaEventRecord(r.a, s);
+}
+static inline void prof_end(HandleImpl* h, cudaStream_t s) {
+    if (!h->prof_on) return;
+    cudaEventRecord(h->recs[h->recs_used].b, s);
+    h->recs_used++;
+}
+// KL(handle, class, stream, kernel<<<...>>>(...)) : count (and optionally time) one launch
+#define KL(h, cls, s, ...)    \
+    do {                      \
+        prof_begin(h, cls, s); \
+        __VA_ARGS__;          \
+        prof_end(h, s);       \
+    } while (0)
 
 template <typename K>
 static cudaError_t set_smem(K kernel, int bytes) {
@@ -54,6 +101,9 @@ extern "C" int cgp_create(cgp_handle** out, int device) {
     h->pinned_used = 0;
     CGP_CHECK(cudaEventCreateWithFlags(&h->ring_event, cudaEventDisableTiming));
     h->ring_event_pending = false;
+    h->prof_on = false;
+    h->recs_used = 0;
+    for (int i = 0; i < CLS_COUNT; ++i) h->ms[i] = 0.0, h->launches[i] = 0;
     CGP_CHECK(set_smem(k_dgemm_nt, GEMM_SMEM_BYTES));
     CGP_CHECK(set_smem(k_potrf_update, GEMM_SMEM_BYTES));
     CGP_CHECK(set_smem(k_potrf_panel, GEMM_SMEM_BYTES));
@@ -69,9 +119,40 @@ extern "C" int cgp_create(cgp_handle** out, int device) {
 extern "C" int cgp_destroy(cgp_handle* hh) {
     if (!hh) return -1;
     HandleImpl* h = static_cast<HandleImpl*>(hh);
+    for (auto& r : h->recs) {
+        cudaEventDestroy(r.a);
+        cudaEventDestroy(r.b);
+    }
     cudaEventDestroy(h->ring_event);
     cudaFreeHost(h->pinned);
     delete h;
+    return 0;
+}
+
+extern "C" int cgp_profile_classes(void) { return CLS_COUNT; }
+extern "C" const char* cgp_profile_class_name(int cls) { return (cls >= 0 && cls < CLS_COUNT) ? kClassNames[cls] : ""; }
+extern "C" int cgp_profile_enable(cgp_handle* hh, int on) {
+    if (!hh) return -1;
+    static_cast<HandleImpl*>(hh)->prof_on = on != 0;
+    return 0;
+}
+// Folds the finished event pairs into ms[] (synchronises on them), copies the totals out and optionally resets.
+extern "C" int cgp_profile_read(cgp_handle* hh, double* ms, int64_t* launches, int n_cls, int reset) {
+    HandleImpl* h = static_cast<HandleImpl*>(hh);
+    if (!h) return -1;
+    for (size_t i = 0; i < h->recs_used; ++i) {
+        float t = 0.f;
+        CGP_CHECK(cudaEventSynchronize(h->recs[i].b));
+        CGP_CHECK(cudaEventElapsedTime(&t, h->recs[i].a, h->recs[i].b));
+        h->ms[h->recs[i].cls] += t;
+    }
+    h->recs_used = 0;
+    for (int i = 0; i < n_cls && i < CLS_COUNT; ++i) {
+        if (ms) ms[i] = h->ms[i];
+        if (launches) launches[i] = h->launches[i];
+    }
+    if (reset)
+        for (int i = 0; i < CLS_COUNT; ++i) h->ms[i] = 0.0, h->launches[i] = 0;
     return 0;
 }
 
@@ -98,32 +179,34 @@ static inline size_t xtile_smem(int d) { return (size_t)2 * CGP_TILE * (d | 1) *
 // ------------------------------------------------------------------------------------------------
 // dense kernel matrices (K1 single-matrix form, cross kernel)
 // ------------------------------------------------------------------------------------------------
-static int launch_cross(int kind, const double* Q, int64_t m, const double* X, int64_t n, int d, const double* theta,
+static int launch_cross(HandleImpl* h, int kind, const double* Q, int64_t m, const double* X, int64_t n, int d, const double* theta,
                         double* out, int64_t ldo, int64_t rows_out, int64_t cols_out, int self, double alpha,
                         cudaStream_t s) {
     dim3 grid((unsigned)((cols_out + CGP_TILE - 1) / CGP_TILE), (unsigned)((rows_out + CGP_TILE - 1) / CGP_TILE));
     if (grid.x == 0 || grid.y == 0) return 0;
     size_t sm = xtile_smem(d);
     if (kind == CGP_KIND_MATERN32)
-        k_cross<0><<<grid, 256, sm, s>>>(Q, m, X, n, d, theta, out, ldo, rows_out, cols_out, self, alpha);
+        KL(h, CLS_CROSS, s, k_cross<0><<<grid, 256, sm, s>>>(Q, m, X, n, d, theta, out, ldo, rows_out, cols_out, self, alpha));
     else
-        k_cross<1><<<grid, 256, sm, s>>>(Q, m, X, n, d, theta, out, ldo, rows_out, cols_out, self, alpha);
+        KL(h, CLS_CROSS, s, k_cross<1><<<grid, 256, sm, s>>>(Q, m, X, n, d, theta, out, ldo, rows_out, cols_out, self, alpha));
     return (int)cudaGetLastError();
 }
 
-extern "C" int cgp_kernel_matrix(cgp_handle* h, int kind, const double* X, int64_t n, int d, const double* theta,
+extern "C" int cgp_kernel_matrix(cgp_handle* hh, int kind, const double* X, int64_t n, int d, const double* theta,
                                  double alpha, double* K, void* stream) {
+    HandleImpl* h = static_cast<HandleImpl*>(hh);
     if (!h) return -1;
     if (kind != 0 && kind != 1) return -2;
     if (!X || n < 0) return -3;
     if (d < 1 || d > CGP_MAX_D) return -5;
     if (!theta) return -6;
     if (!K) return -8;
-    return launch_cross(kind, X, n, X, n, d, theta, K, n, n, n, 1, alpha, (cudaStream_t)stream);
+    return launch_cross(h, kind, X, n, X, n, d, theta, K, n, n, n, 1, alpha, (cudaStream_t)stream);
 }
 
-extern "C" int cgp_kernel_cross(cgp_handle* h, int kind, const double* Q, int64_t m, const double* X, int64_t n, int d,
+extern "C" int cgp_kernel_cross(cgp_handle* hh, int kind, const double* Q, int64_t m, const double* X, int64_t n, int d,
                                 const double* theta, double* Kqx, void* stream) {
+    HandleImpl* h = static_cast<HandleImpl*>(hh);
     if (!h) return -1;
     if (kind != 0 && kind != 1) return -2;
     if (!Q || m < 0) return -3;
@@ -131,16 +214,18 @@ extern "C" int cgp_kernel_cross(cgp_handle* h, int kind, const double* Q, int64_
     if (d < 1 || d > CGP_MAX_D) return -7;
     if (!theta) return -8;
     if (!Kqx) return -9;
-    return launch_cross(kind, Q, m, X, n, d, theta, Kqx, n, m, n, 0, 0.0, (cudaStream_t)stream);
+    return launch_cross(h, kind, Q, m, X, n, d, theta, Kqx, n, m, n, 0, 0.0, (cudaStream_t)stream);
 }
 
-extern "C" int cgp_dgemm_nt(cgp_handle* h, const double* A, const double* B, double* C, int64_t M, int64_t N, int64_t K,
+extern "C" int cgp_dgemm_nt(cgp_handle* hh, const double* A, const double* B, double* C, int64_t M, int64_t N, int64_t K,
                             void* stream) {
+    HandleImpl* h = static_cast<HandleImpl*>(hh);
     if (!h) return -1;
     if (!A || !B || !C) return -2;
     if (M <= 0 || M % CGP_TILE || N <= 0 || N % CGP_TILE || K <= 0 || K % CGP_BK) return -5;
     dim3 grid((unsigned)(N / CGP_TILE), (unsigned)(M / CGP_TILE));
-    k_dgemm_nt<<<grid, CGP_GEMM_THREADS, GEMM_SMEM_BYTES, (cudaStream_t)stream>>>(A, B, C, M, N, (int)K);
+    cudaStream_t s = (cudaStream_t)stream;
+    KL(h, CLS_DGEMM, s, k_dgemm_nt<<<grid, CGP_GEMM_THREADS, GEMM_SMEM_BYTES, s>>>(A, B, C, M, N, (int)K));
     return (int)cudaGetLastError();
 }
 
@@ -154,34 +239,34 @@ struct Batch {
 };
 
 // assemble -> blocked Cholesky -> U = L^-T -> z, a, lml [-> K^-1 -> gradient]
-static int run_pipeline(int kind, const double* X, const double* y, const double* theta, double alpha, int d,
+static int run_pipeline(HandleImpl* h, int kind, const double* X, const double* y, const double* theta, double alpha, int d,
                         const Batch& b, double* lml, double* grad, int* info, cudaStream_t s) {
     const int nm = b.nm, T = b.Tmax;
     const size_t xs = xtile_smem(d);
     dim3 gl(b.ntl_max, nm);
     if (kind == 0)
-        k_assemble<0><<<gl, 256, xs, s>>>(b.A, X, theta, b.meta, d, alpha);
+        KL(h, CLS_ASSEMBLE, s, k_assemble<0><<<gl, 256, xs, s>>>(b.A, X, theta, b.meta, d, alpha));
     else
-        k_assemble<1><<<gl, 256, xs, s>>>(b.A, X, theta, b.meta, d, alpha);
+        KL(h, CLS_ASSEMBLE, s, k_assemble<1><<<gl, 256, xs, s>>>(b.A, X, theta, b.meta, d, alpha));
     for (int j = 0; j < T; ++j) {
-        if (j > 0) k_potrf_update<<<dim3(T - j, nm), CGP_GEMM_THREADS, GEMM_SMEM_BYTES, s>>>(b.A, b.meta, j);
-        k_potrf_diag<<<nm, 256, DIAG_SMEM_BYTES, s>>>(b.A, b.U, b.D, b.logdet, info, b.meta, j, T);
-        if (j + 1 < T) k_potrf_panel<<<dim3(T - j - 1, nm), CGP_GEMM_THREADS, GEMM_SMEM_BYTES, s>>>(b.A, b.D, b.meta, j);
+        if (j > 0) KL(h, CLS_POTRF_UPDATE, s, k_potrf_update<<<dim3(T - j, nm), CGP_GEMM_THREADS, GEMM_SMEM_BYTES, s>>>(b.A, b.meta, j));
+        KL(h, CLS_POTRF_DIAG, s, k_potrf_diag<<<nm, 256, DIAG_SMEM_BYTES, s>>>(b.A, b.U, b.D, b.logdet, info, b.meta, j, T));
+        if (j + 1 < T) KL(h, CLS_POTRF_PANEL, s, k_potrf_panel<<<dim3(T - j - 1, nm), CGP_GEMM_THREADS, GEMM_SMEM_BYTES, s>>>(b.A, b.D, b.meta, j));
     }
     for (int i = 1; i < T; ++i) {
-        k_trtri_acc<<<dim3(i, nm), CGP_GEMM_THREADS, GEMM_SMEM_BYTES, s>>>(b.A, b.U, b.meta, i);
-        k_trtri_scale<<<dim3(i, nm), CGP_GEMM_THREADS, GEMM_SMEM_BYTES, s>>>(b.U, b.D, b.meta, i);
+        KL(h, CLS_TRTRI_ACC, s, k_trtri_acc<<<dim3(i, nm), CGP_GEMM_THREADS, GEMM_SMEM_BYTES, s>>>(b.A, b.U, b.meta, i));
+        KL(h, CLS_TRTRI_SCALE, s, k_trtri_scale<<<dim3(i, nm), CGP_GEMM_THREADS, GEMM_SMEM_BYTES, s>>>(b.U, b.D, b.meta, i));
     }
-    k_solve_z<<<dim3(T, nm), 128, 0, s>>>(b.U, y, b.z, b.meta, b.npad_max);
-    k_solve_a<<<dim3(b.npad_max / 8, nm), 256, 0, s>>>(b.U, b.z, b.a, b.meta, b.npad_max);
-    k_lml_finish<<<nm, 256, 0, s>>>(b.z, b.logdet, info, lml, b.meta, b.npad_max, T);
+    KL(h, CLS_SOLVE, s, k_solve_z<<<dim3(T, nm), 128, 0, s>>>(b.U, y, b.z, b.meta, b.npad_max));
+    KL(h, CLS_SOLVE, s, k_solve_a<<<dim3(b.npad_max / 8, nm), 256, 0, s>>>(b.U, b.z, b.a, b.meta, b.npad_max));
+    KL(h, CLS_SOLVE, s, k_lml_finish<<<nm, 256, 0, s>>>(b.z, b.logdet, info, lml, b.meta, b.npad_max, T));
     if (grad) {
-        k_lauum<<<gl, CGP_GEMM_THREADS, GEMM_SMEM_BYTES, s>>>(b.A, b.U, b.meta);
+        KL(h, CLS_LAUUM, s, k_lauum<<<gl, CGP_GEMM_THREADS, GEMM_SMEM_BYTES, s>>>(b.A, b.U, b.meta));
         const int dm = dmax_for(d);
         const size_t gs = xs + (2 * CGP_TILE + 8 * dm) * 8;
 #define LAUNCH_GRAD(KIND, DM)                                                                                        \
-    k_grad_tiles<KIND, DM><<<gl, 256, gs, s>>>(b.A, X, b.a, theta, b.gpart, b.meta, d, b.npad_max, b.ntl_max);       \
-    k_grad_finish<DM><<<nm, 256, 0, s>>>(b.A, b.a, b.gpart, theta, info, grad, b.meta, d, b.npad_max, b.ntl_max)
+    KL(h, CLS_GRAD, s, (k_grad_tiles<KIND, DM><<<gl, 256, gs, s>>>(b.A, X, b.a, theta, b.gpart, b.meta, d, b.npad_max, b.ntl_max))); \
+    KL(h, CLS_GRAD, s, (k_grad_finish<DM><<<nm, 256, 0, s>>>(b.A, b.a, b.gpart, theta, info, grad, b.meta, d, b.npad_max, b.ntl_max)))
         if (kind == 0) {
             if (dm == 4) { LAUNCH_GRAD(0, 4); } else if (dm == 8) { LAUNCH_GRAD(0, 8); } else { LAUNCH_GRAD(0, 16); }
         } else {
@@ -306,7 +391,7 @@ extern "C" int cgp_lml_grad_batched(cgp_handle* hh, int kind, const double* X, c
         }
         int rc = upload(h, b.meta, &metas[m0], (size_t)(m1 - m0) * sizeof(MatMeta), s);
         if (rc) return rc;
-        rc = run_pipeline(kind, X, y, theta, alpha, d, b, lml, grad, info, s);
+        rc = run_pipeline(h, kind, X, y, theta, alpha, d, b, lml, grad, info, s);
         if (rc) return rc;
         m0 = m1;
     }
@@ -377,10 +462,10 @@ extern "C" int cgp_factorize(cgp_handle* hh, int kind, const double* X, const do
     CGP_CHECK(cudaMemsetAsync(b.U, 0, (size_t)elems * 8, s));
     int rc = upload(h, b.meta, metas.data(), (size_t)C * sizeof(MatMeta), s);
     if (rc) return rc;
-    rc = run_pipeline(kind, X, y, theta, alpha, d, b, lml, nullptr, info, s);
+    rc = run_pipeline(h, kind, X, y, theta, alpha, d, b, lml, nullptr, info, s);
     if (rc) return rc;
-    k_transpose<<<dim3(b.npad_max / 32, b.npad_max / 32, C), dim3(32, 8), 0, s>>>(b.U, W, b.meta);
-    k_gather_alpha<<<dim3((b.npad_max + 255) / 256, C), 256, 0, s>>>(b.a, alpha_vec, b.meta, b.npad_max);
+    KL(h, CLS_TRANSPOSE, s, k_transpose<<<dim3(b.npad_max / 32, b.npad_max / 32, C), dim3(32, 8), 0, s>>>(b.U, W, b.meta));
+    KL(h, CLS_SOLVE, s, k_gather_alpha<<<dim3((b.npad_max + 255) / 256, C), 256, 0, s>>>(b.a, alpha_vec, b.meta, b.npad_max));
     return (int)cudaGetLastError();
 }
 
@@ -388,7 +473,7 @@ extern "C" int cgp_factorize(cgp_handle* hh, int kind, const double* X, const do
 // k-NN routing
 // ------------------------------------------------------------------------------------------------
 template <int D>
-static int launch_knn(const double* X, const long long* lab, int n, int k, const double* Q, long long M, long long* out,
+static int launch_knn(HandleImpl* h, const double* X, const long long* lab, int n, int k, const double* Q, long long M, long long* out,
                       cudaStream_t s) {
     size_t sm = (size_t)KNN_TILE * D * 8 + KNN_TILE * 4;
     if (sm > 48 * 1024) {
@@ -396,12 +481,13 @@ static int launch_knn(const double* X, const long long* lab, int n, int k, const
         if (e != cudaSuccess) return (int)e;
     }
     unsigned grid = (unsigned)((M + KNN_THREADS - 1) / KNN_THREADS);
-    k_knn<D><<<grid, KNN_THREADS, sm, s>>>(X, lab, n, k, Q, M, out);
+    KL(h, CLS_KNN, s, k_knn<D><<<grid, KNN_THREADS, sm, s>>>(X, lab, n, k, Q, M, out));
     return (int)cudaGetLastError();
 }
 
-extern "C" int cgp_knn_labels(cgp_handle* h, const double* X, const int64_t* labels, int64_t n, int d, int k, int n_classes,
+extern "C" int cgp_knn_labels(cgp_handle* hh, const double* X, const int64_t* labels, int64_t n, int d, int k, int n_classes,
                               const double* Q, int64_t m, int64_t* out, void* stream) {
+    HandleImpl* h = static_cast<HandleImpl*>(hh);
     if (!h) return -1;
     if (!X) return -2;
     if (!labels) return -3;
@@ -419,7 +505,7 @@ extern "C" int cgp_knn_labels(cgp_handle* h, const double* X, const int64_t* lab
     switch (d) {
 #define KNN_CASE(D) \
     case D:         \
-        return launch_knn<D>(X, lab, (int)n, k, Q, m, o, s);
+        return launch_knn<D>(h, X, lab, (int)n, k, Q, m, o, s);
         KNN_CASE(1) KNN_CASE(2) KNN_CASE(3) KNN_CASE(4) KNN_CASE(5) KNN_CASE(6) KNN_CASE(7) KNN_CASE(8)
         KNN_CASE(9) KNN_CASE(10) KNN_CASE(11) KNN_CASE(12) KNN_CASE(13) KNN_CASE(14) KNN_CASE(15) KNN_CASE(16)
 #undef KNN_CASE
@@ -497,9 +583,9 @@ static int run_score(HandleImpl* h, int kind, const double* X, const int64_t* of
     double* mraw = reinterpret_cast<double*>(ws + L.o_mraw);
     const long long* ql = reinterpret_cast<const long long*>(qlabel);
 
-    k_bucket_hist<<<L.nblk, 256, (size_t)C * 4, s>>>(ql, m, C, L.nblk, hist);
-    k_bucket_scan<<<1, 1024, 0, s>>>(hist, blkoff, coff, C, L.nblk);
-    k_bucket_scatter<<<L.nblk, 32, (size_t)C * 8, s>>>(ql, Q, m, C, L.nblk, d, blkoff, perm, Qs);
+    KL(h, CLS_BUCKET, s, k_bucket_hist<<<L.nblk, 256, (size_t)C * 4, s>>>(ql, m, C, L.nblk, hist));
+    KL(h, CLS_BUCKET, s, k_bucket_scan<<<1, 1024, 0, s>>>(hist, blkoff, coff, C, L.nblk));
+    KL(h, CLS_BUCKET, s, k_bucket_scatter<<<L.nblk, 32, (size_t)C * 8, s>>>(ql, Q, m, C, L.nblk, d, blkoff, perm, Qs));
     CGP_CHECK(cudaGetLastError());
     std::vector<long long> hoff(C + 1);
     CGP_CHECK(cudaMemcpyAsync(hoff.data(), coff, (size_t)(C + 1) * 8, cudaMemcpyDeviceToHost, s));
@@ -518,22 +604,21 @@ static int run_score(HandleImpl* h, int kind, const double* X, const int64_t* of
         for (long long p0 = hoff[c]; p0 < hoff[c + 1]; p0 += L.mch) {
             const long long rows = std::min<long long>(L.mch, hoff[c + 1] - p0);
             const long long rows_pad = pad_n(rows);
-            int rc = launch_cross(kind, Qs + p0 * d, rows, Xc, n, d, th, kstar, npad, rows_pad, npad, 0, 0.0, s);
+            int rc = launch_cross(h, kind, Qs + p0 * d, rows, Xc, n, d, th, kstar, npad, rows_pad, npad, 0, 0.0, s);
             if (rc) return rc;
-            k_mean<<<(unsigned)((rows + 7) / 8), 256, 0, s>>>(kstar, alpha_vec + offs[c], (int)n, (int)npad, rows, mraw);
-            k_predict_vnorm<<<(unsigned)((rows_pad / CGP_TILE) * T), CGP_GEMM_THREADS, GEMM_SMEM_BYTES, s>>>(
-                Wc, kstar, vpart, (int)npad, L.mch);
-            k_score_finish<<<(unsigned)((rows + 255) / 256), 256, 0, s>>>(vpart, L.mch, T, mraw, rows, p0, perm, th, d,
-                                                                          y_mean, y_std, y_max, c, 0.0, (double)n, mean,
-                                                                          std_, score, sorted);
+            KL(h, CLS_MEAN, s, k_mean<<<(unsigned)((rows + 7) / 8), 256, 0, s>>>(kstar, alpha_vec + offs[c], (int)n, (int)npad, rows, mraw));
+            KL(h, CLS_PREDICT_VNORM, s, k_predict_vnorm<<<(unsigned)((rows_pad / CGP_TILE) * T), CGP_GEMM_THREADS, GEMM_SMEM_BYTES, s>>>(
+                Wc, kstar, vpart, (int)npad, L.mch));
+            KL(h, CLS_SCORE_FINISH, s, k_score_finish<<<(unsigned)((rows + 255) / 256), 256, 0, s>>>(
+                vpart, L.mch, T, mraw, rows, p0, perm, th, d, y_mean, y_std, y_max, c, (double)n, mean, std_, score, sorted));
         }
     }
     if (y_max && best_score && best_idx && best_cluster) {
         int nb = (int)std::min<long long>(1024, (m + 255) / 256);
         if (nb < 1) nb = 1;
-        k_argmax_blocks<<<nb, 256, 0, s>>>(sorted, m, blkv, blkp);
-        k_argmax_final<<<1, 256, 0, s>>>(blkv, blkp, nb, perm, coff, C, idx_base, best_score, reinterpret_cast<long long*>(best_idx),
-                                         reinterpret_cast<long long*>(best_cluster));
+        KL(h, CLS_ARGMAX, s, k_argmax_blocks<<<nb, 256, 0, s>>>(sorted, m, blkv, blkp));
+        KL(h, CLS_ARGMAX, s, k_argmax_final<<<1, 256, 0, s>>>(blkv, blkp, nb, perm, coff, C, idx_base, best_score, reinterpret_cast<long long*>(best_idx),
+                                         reinterpret_cast<long long*>(best_cluster)));
     }
     return (int)cudaGetLastError();
 }

@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(256)
 k_score_finish(const double* __restrict__ vpart, long long vstride, int T, const double* __restrict__ mraw,
                long long rows, long long pos0, const long long* __restrict__ perm, const double* __restrict__ th, int d,
                const double* __restrict__ ymean, const double* __restrict__ ystd, const double* __restrict__ ymax,
-               int cluster, double inv_unused, double n_c, double* __restrict__ mean_out, double* __restrict__ std_out,
+               int cluster, double n_c, double* __restrict__ mean_out, double* __restrict__ std_out,
                double* __restrict__ score_out, double* __restrict__ score_sorted) {
     const long long r = (long long)blockIdx.x * 256 + threadIdx.x;
     if (r >= rows) return;

@@ -125,6 +125,14 @@ int cgp_ei_argmax(cgp_handle* h, int kind, const double* X, const int64_t* offs_
 int cgp_dgemm_nt(cgp_handle* h, const double* A, const double* B, double* C, int64_t M, int64_t N,
                  int64_t K, void* stream);
 
+/* Measurement: every kernel launch is counted per kernel class; with profiling enabled each launch is also
+ * bracketed by CUDA events on the caller's stream.  cgp_profile_read() folds the finished events into per-class
+ * totals (milliseconds) and returns them with the launch counts (arrays of cgp_profile_classes() entries). */
+int cgp_profile_classes(void);
+const char* cgp_profile_class_name(int cls);
+int cgp_profile_enable(cgp_handle* h, int on);
+int cgp_profile_read(cgp_handle* h, double* ms, int64_t* launches, int n_cls, int reset);
+
 #ifdef __cplusplus
 }
 #endif
