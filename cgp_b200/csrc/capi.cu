@@ -1,6 +1,7 @@
 // C-ABI of cgp_b200 (see include/cgp_b200.h).  Host-side orchestration only: every entry point is a
 // fixed sequence of asynchronous kernel launches on the caller's stream.
 #include <cstdio>
+#include <algorithm>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -20,12 +21,14 @@ static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; 
 static inline int64_t pad_n(int64_t n) { return (n + CGP_TILE - 1) / CGP_TILE * CGP_TILE; }
 
 enum {
-    CLS_ASSEMBLE, CLS_POTRF_UPDATE, CLS_POTRF_DIAG, CLS_POTRF_PANEL, CLS_TRTRI_ACC, CLS_TRTRI_SCALE, CLS_SOLVE,
+    CLS_ASSEMBLE, CLS_POTRF_UPDATE, CLS_POTRF_TRAIL, CLS_POTRF_DIAG, CLS_POTRF_PANEL, CLS_TRTRI_ACC, CLS_TRTRI_TRAIL,
+    CLS_TRTRI_SCALE, CLS_SOLVE,
     CLS_LAUUM, CLS_GRAD, CLS_TRANSPOSE, CLS_KNN, CLS_BUCKET, CLS_CROSS, CLS_MEAN, CLS_PREDICT_VNORM,
     CLS_SCORE_FINISH, CLS_ARGMAX, CLS_DGEMM, CLS_COUNT
 };
 static const char* const kClassNames[CLS_COUNT] = {
-    "assemble", "potrf_update", "potrf_diag", "potrf_panel", "trtri_acc", "trtri_scale", "solve_lml",
+    "assemble", "potrf_update", "potrf_trail", "potrf_diag", "potrf_panel", "trtri_acc", "trtri_trail",
+    "trtri_scale", "solve_lml",
     "lauum", "grad", "transpose", "knn", "bucket", "cross", "mean", "predict_vnorm",
     "score_finish", "argmax", "dgemm_nt"};
 
@@ -107,6 +110,8 @@ extern "C" int cgp_create(cgp_handle** out, int device) {
     CGP_CHECK(set_smem(k_dgemm_nt, GEMM_SMEM_BYTES));
     CGP_CHECK(set_smem(k_potrf_update, GEMM_SMEM_BYTES));
     CGP_CHECK(set_smem(k_potrf_panel, GEMM_SMEM_BYTES));
+    CGP_CHECK(set_smem(k_potrf_trail, GEMM_SMEM_BYTES));
+    CGP_CHECK(set_smem(k_trtri_trail, GEMM_SMEM_BYTES));
     CGP_CHECK(set_smem(k_trtri_acc, GEMM_SMEM_BYTES));
     CGP_CHECK(set_smem(k_trtri_scale, GEMM_SMEM_BYTES));
     CGP_CHECK(set_smem(k_lauum, GEMM_SMEM_BYTES));
@@ -248,14 +253,29 @@ static int run_pipeline(HandleImpl* h, int kind, const double* X, const double* 
         KL(h, CLS_ASSEMBLE, s, k_assemble<0><<<gl, 256, xs, s>>>(b.A, X, theta, b.meta, d, alpha));
     else
         KL(h, CLS_ASSEMBLE, s, k_assemble<1><<<gl, 256, xs, s>>>(b.A, X, theta, b.meta, d, alpha));
-    for (int j = 0; j < T; ++j) {
-        if (j > 0) KL(h, CLS_POTRF_UPDATE, s, k_potrf_update<<<dim3(T - j, nm), CGP_GEMM_THREADS, GEMM_SMEM_BYTES, s>>>(b.A, b.meta, j));
-        KL(h, CLS_POTRF_DIAG, s, k_potrf_diag<<<nm, 256, DIAG_SMEM_BYTES, s>>>(b.A, b.U, b.D, b.logdet, info, b.meta, j, T));
-        if (j + 1 < T) KL(h, CLS_POTRF_PANEL, s, k_potrf_panel<<<dim3(T - j - 1, nm), CGP_GEMM_THREADS, GEMM_SMEM_BYTES, s>>>(b.A, b.D, b.meta, j));
+    for (int c0 = 0; c0 < T; c0 += CGP_PANEL) {
+        const int c1 = std::min(T, c0 + CGP_PANEL);
+        for (int j = c0; j < c1; ++j) {
+            if (j > c0)
+                KL(h, CLS_POTRF_UPDATE, s, k_potrf_update<<<dim3(T - j, nm), CGP_GEMM_THREADS, GEMM_SMEM_BYTES, s>>>(b.A, b.meta, j, c0));
+            KL(h, CLS_POTRF_DIAG, s, k_potrf_diag<<<nm, 256, DIAG_SMEM_BYTES, s>>>(b.A, b.U, b.D, b.logdet, info, b.meta, j, T));
+            if (j + 1 < T)
+                KL(h, CLS_POTRF_PANEL, s, k_potrf_panel<<<dim3(T - j - 1, nm), CGP_GEMM_THREADS, GEMM_SMEM_BYTES, s>>>(b.A, b.D, b.meta, j));
+        }
+        if (c1 < T) {
+            const int Tt = T - c1;
+            KL(h, CLS_POTRF_TRAIL, s, k_potrf_trail<<<dim3(Tt * (Tt + 1) / 2, nm), CGP_GEMM_THREADS, GEMM_SMEM_BYTES, s>>>(b.A, b.meta, c0, c1));
+        }
     }
-    for (int i = 1; i < T; ++i) {
-        KL(h, CLS_TRTRI_ACC, s, k_trtri_acc<<<dim3(i, nm), CGP_GEMM_THREADS, GEMM_SMEM_BYTES, s>>>(b.A, b.U, b.meta, i));
-        KL(h, CLS_TRTRI_SCALE, s, k_trtri_scale<<<dim3(i, nm), CGP_GEMM_THREADS, GEMM_SMEM_BYTES, s>>>(b.U, b.D, b.meta, i));
+    for (int c0 = 0; c0 < T; c0 += CGP_PANEL) {
+        const int c1 = std::min(T, c0 + CGP_PANEL);
+        for (int i = std::max(c0, 1); i < c1; ++i) {
+            if (i > c0)
+                KL(h, CLS_TRTRI_ACC, s, k_trtri_acc<<<dim3(i, nm), CGP_GEMM_THREADS, GEMM_SMEM_BYTES, s>>>(b.A, b.U, b.meta, i, c0));
+            KL(h, CLS_TRTRI_SCALE, s, k_trtri_scale<<<dim3(i, nm), CGP_GEMM_THREADS, GEMM_SMEM_BYTES, s>>>(b.U, b.D, b.meta, i));
+        }
+        if (c1 < T)
+            KL(h, CLS_TRTRI_TRAIL, s, k_trtri_trail<<<dim3(c1 * (T - c1), nm), CGP_GEMM_THREADS, GEMM_SMEM_BYTES, s>>>(b.A, b.U, b.meta, c0, c1, T));
     }
     KL(h, CLS_SOLVE, s, k_solve_z<<<dim3(T, nm), 128, 0, s>>>(b.U, y, b.z, b.meta, b.npad_max));
     KL(h, CLS_SOLVE, s, k_solve_a<<<dim3(b.npad_max / 8, nm), 256, 0, s>>>(b.U, b.z, b.a, b.meta, b.npad_max));

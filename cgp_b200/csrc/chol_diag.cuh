@@ -1,7 +1,14 @@
-// Diagonal-block kernel of the blocked Cholesky: one CTA factorises a 128x128 block held in shared
-// memory (unblocked right-looking dpotf2), writes L_jj, then inverts it in place (dtrti2) and writes
-// D_j = inv(L_jj) (row-major, for the panel GEMMs) and U_jj = D_j^T (the diagonal block of U = L^-T).
-// Also the whole factorisation for clusters with n <= 128 ("one CTA per matrix").
+// Diagonal-block kernel of the blocked Cholesky: one CTA factorises a 128x128 block held in shared memory,
+// writes L_jj, inverts it in place and writes D_j = inv(L_jj) (row-major, the B operand of the panel GEMMs)
+// and U_jj = D_j^T (the diagonal block of U = L^-T).  For clusters with n <= 128 this is the whole
+// factorisation ("one CTA per matrix").
+//
+// Both steps are blocked by 32 so that almost all flops run as register-tiled updates between few barriers:
+//   potrf: per 32-column sub-block  (1) one warp factors the 32x32 diagonal piece in registers with
+//          warp-shuffle column broadcasts, (2) one thread per row solves the sub-panel below it,
+//          (3) all threads apply the rank-32 update to the trailing part in 4x4 register tiles;
+//   trtri: the four 32x32 diagonal pieces are inverted by four warps (one lane per column), the off-diagonal
+//          32x32 pieces follow column-block by column-block as small register-tiled products.
 #pragma once
 #include "common.cuh"
 
@@ -18,76 +25,218 @@ k_potrf_diag(double* __restrict__ Abuf, double* __restrict__ Ubuf, double* __res
     const MatMeta m = meta[blockIdx.x];
     const int T = m.npad / CGP_TILE;
     if (j >= T) return;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const long long ld = m.npad;
     double* S = diag_smem;
-    double* tmp = diag_smem + CGP_TILE * DIAG_LD;
+    double* rinv = diag_smem + CGP_TILE * DIAG_LD;
     double* tile = Abuf + m.a_off + (long long)j * CGP_TILE * ld + (long long)j * CGP_TILE;
     __shared__ int fail;
     if (tid == 0) fail = 0;
-    for (int idx = tid; idx < CGP_TILE * CGP_TILE; idx += 256) {
-        int r = idx >> 7, c = idx & 127;
-        S[r * DIAG_LD + c] = tile[(long long)r * ld + c];
+    for (int idx = tid; idx < CGP_TILE * CGP_TILE / 2; idx += 256) {
+        int r = idx >> 6, c = (idx & 63) * 2;
+        double2 v = *reinterpret_cast<const double2*>(tile + (long long)r * ld + c);
+        S[r * DIAG_LD + c] = v.x;
+        S[r * DIAG_LD + c + 1] = v.y;
     }
     __syncthreads();
 
-    // ---- dpotf2 (lower), right-looking
-    const int tx = tid & 15, ty = tid >> 4;
-    for (int c = 0; c < CGP_TILE; ++c) {
-        if (tid == 0) {
-            double p = S[c * DIAG_LD + c];
-            if (!(p > 0.0) && fail == 0) fail = c + 1;
-            S[c * DIAG_LD + c] = sqrt(p);
+    // ---------------- potrf, blocked by 32
+    for (int k0 = 0; k0 < CGP_TILE; k0 += 32) {
+        if (warp == 0) {
+            double row[32];
+#pragma unroll
+            for (int q = 0; q < 32; ++q) row[q] = (q <= lane) ? S[(k0 + lane) * DIAG_LD + k0 + q] : 0.0;
+            int failcol = -1;
+            double dinv = 0.0;
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+                const double dcc = __shfl_sync(0xffffffffu, row[c], c);
+                if (!(dcc > 0.0) && failcol < 0) failcol = c;
+                const double ip = rsqrt(dcc);
+                const double lc = (lane == c) ? dcc * ip : row[c] * ip;
+                row[c] = lc;
+                if (lane == c) dinv = ip;
+#pragma unroll
+                for (int q = c + 1; q < 32; ++q) {
+                    const double lq = __shfl_sync(0xffffffffu, lc, q);
+                    if (lane >= q) row[q] -= lc * lq;
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 32; ++q)
+                if (q <= lane) S[(k0 + lane) * DIAG_LD + k0 + q] = row[q];
+            rinv[k0 + lane] = dinv;
+            if (lane == 0 && failcol >= 0 && fail == 0) fail = k0 + failcol + 1;
         }
         __syncthreads();
-        const double piv = S[c * DIAG_LD + c];
-        for (int r = c + 1 + tid; r < CGP_TILE; r += 256) S[r * DIAG_LD + c] /= piv;
+        const int mrem = CGP_TILE - k0 - 32;
+        if (tid < mrem) {  // sub-panel: rows below the diagonal piece, forward substitution
+            const int r = k0 + 32 + tid;
+            double x[32];
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+                double sacc = S[r * DIAG_LD + k0 + c];
+#pragma unroll
+                for (int q = 0; q < c; ++q) sacc -= x[q] * S[(k0 + c) * DIAG_LD + k0 + q];
+                x[c] = sacc * rinv[k0 + c];
+            }
+#pragma unroll
+            for (int c = 0; c < 32; ++c) S[r * DIAG_LD + k0 + c] = x[c];
+        }
         __syncthreads();
-        for (int r = c + 1 + ty; r < CGP_TILE; r += 16) {
-            const double lr = S[r * DIAG_LD + c];
-            for (int q = c + 1 + tx; q <= r; q += 16) S[r * DIAG_LD + q] -= lr * S[q * DIAG_LD + c];
+        const int nsub = mrem / 4, cnt = nsub * (nsub + 1) / 2;
+        for (int st = tid; st < cnt; st += 256) {  // rank-32 update of the trailing lower part, 4x4 register tiles
+            int a = (int)((sqrtf(8.0f * (float)st + 1.0f) - 1.0f) * 0.5f);
+            while (a * (a + 1) / 2 > st) --a;
+            while ((a + 1) * (a + 2) / 2 <= st) ++a;
+            const int b = st - a * (a + 1) / 2;
+            const int r0 = k0 + 32 + 4 * a, q0 = k0 + 32 + 4 * b;
+            double acc[4][4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) acc[i][jj] = 0.0;
+#pragma unroll 4
+            for (int c = 0; c < 32; ++c) {
+                double ra[4], rb[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    ra[i] = S[(r0 + i) * DIAG_LD + k0 + c];
+                    rb[i] = S[(q0 + i) * DIAG_LD + k0 + c];
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj) acc[i][jj] += ra[i] * rb[jj];
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) S[(r0 + i) * DIAG_LD + q0 + jj] -= acc[i][jj];
         }
         __syncthreads();
     }
 
-    // ---- write L_jj (upper part zeroed), log-determinant partial, status
+    // ---------------- zero the strict upper part, write L_jj, log-determinant partial, status
     for (int idx = tid; idx < CGP_TILE * CGP_TILE; idx += 256) {
         int r = idx >> 7, c = idx & 127;
-        tile[(long long)r * ld + c] = (c <= r) ? S[r * DIAG_LD + c] : 0.0;
+        if (c > r) S[r * DIAG_LD + c] = 0.0;
+    }
+    __syncthreads();
+    for (int idx = tid; idx < CGP_TILE * CGP_TILE / 2; idx += 256) {
+        int r = idx >> 6, c = (idx & 63) * 2;
+        double2 v;
+        v.x = S[r * DIAG_LD + c];
+        v.y = S[r * DIAG_LD + c + 1];
+        *reinterpret_cast<double2*>(tile + (long long)r * ld + c) = v;
     }
     if (tid < 32) {
-        double s = 0.0;
+        double sl = 0.0;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) s += log(S[(tid + 32 * q) * DIAG_LD + tid + 32 * q]);
-        s = warp_sum(s);
+        for (int q = 0; q < 4; ++q) sl += log(S[(tid + 32 * q) * DIAG_LD + tid + 32 * q]);
+        sl = warp_sum(sl);
         if (tid == 0) {
-            logdet_part[(long long)blockIdx.x * Tmax + j] = s;
+            logdet_part[(long long)blockIdx.x * Tmax + j] = sl;
             if (fail != 0 && info[m.out_idx] == 0) info[m.out_idx] = j * CGP_TILE + fail;
         }
     }
+    __syncthreads();
 
-    // ---- dtrti2 (lower, non-unit) in place: columns from last to first
-    for (int jj = CGP_TILE - 1; jj >= 0; --jj) {
-        __syncthreads();
-        if (tid > jj && tid < CGP_TILE) tmp[tid] = S[tid * DIAG_LD + jj];
-        const double djj = 1.0 / S[jj * DIAG_LD + jj];
-        __syncthreads();
-        const int i = jj + 1 + (tid >> 1), h = tid & 1;
-        double s = 0.0;
-        if (i < CGP_TILE)
-            for (int k = jj + 1 + h; k <= i; k += 2) s += S[i * DIAG_LD + k] * tmp[k];
-        s += __shfl_xor_sync(0xffffffffu, s, 1);
-        if (i < CGP_TILE && h == 0) S[i * DIAG_LD + jj] = -s * djj;
-        if (tid == 0) S[jj * DIAG_LD + jj] = djj;
+    // ---------------- trtri (lower, in place), blocked by 32
+    if (warp < 4) {  // the four diagonal pieces: lane = column, forward substitution against e_lane
+        const int k0 = warp * 32;
+        double x[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            double sacc = (i == lane) ? 1.0 : 0.0;
+#pragma unroll
+            for (int k = 0; k < i; ++k) sacc -= S[(k0 + i) * DIAG_LD + k0 + k] * x[k];
+            x[i] = sacc * rinv[k0 + i];
+        }
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+            if (i >= lane) S[(k0 + i) * DIAG_LD + k0 + lane] = x[i];
     }
     __syncthreads();
+    for (int b = 2; b >= 0; --b) {
+        // phase 1: T[a,b] = sum_{a'=b+1}^{a} W[a,a'] L[a',b]   for a = b+1..3  (W trailing part already inverted)
+        const int blk = tid >> 6, sub = tid & 63;
+        const int a = b + 1 + blk;
+        const int ti = sub >> 3, tj = sub & 7;
+        const bool act = a <= 3;
+        double acc[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) acc[i][jj] = 0.0;
+        if (act) {
+            for (int ap = b + 1; ap <= a; ++ap) {
+#pragma unroll 4
+                for (int k = 0; k < 32; ++k) {
+                    double wa[4], lb[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        wa[i] = S[(32 * a + 4 * ti + i) * DIAG_LD + 32 * ap + k];
+                        lb[i] = S[(32 * ap + k) * DIAG_LD + 32 * b + 4 * tj + i];
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+#pragma unroll
+                        for (int jj = 0; jj < 4; ++jj) acc[i][jj] += wa[i] * lb[jj];
+                }
+            }
+        }
+        __syncthreads();
+        if (act) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) S[(32 * a + 4 * ti + i) * DIAG_LD + 32 * b + 4 * tj + jj] = acc[i][jj];
+        }
+        __syncthreads();
+        // phase 2: W[a,b] = -T[a,b] W[b,b]
+        if (act) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) acc[i][jj] = 0.0;
+#pragma unroll 4
+            for (int k = 0; k < 32; ++k) {
+                double ta[4], wb[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    ta[i] = S[(32 * a + 4 * ti + i) * DIAG_LD + 32 * b + k];
+                    wb[i] = S[(32 * b + k) * DIAG_LD + 32 * b + 4 * tj + i];
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj) acc[i][jj] += ta[i] * wb[jj];
+            }
+        }
+        __syncthreads();
+        if (act) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) S[(32 * a + 4 * ti + i) * DIAG_LD + 32 * b + 4 * tj + jj] = -acc[i][jj];
+        }
+        __syncthreads();
+    }
 
     double* D = Dbuf + m.d_off + (long long)j * CGP_TILE * CGP_TILE;
     double* Ut = Ubuf + m.u_off + (long long)j * CGP_TILE * ld + (long long)j * CGP_TILE;
-    for (int idx = tid; idx < CGP_TILE * CGP_TILE; idx += 256) {
-        int r = idx >> 7, c = idx & 127;
-        D[r * CGP_TILE + c] = (c <= r) ? S[r * DIAG_LD + c] : 0.0;
-        Ut[(long long)r * ld + c] = (c >= r) ? S[c * DIAG_LD + r] : 0.0;
+    for (int idx = tid; idx < CGP_TILE * CGP_TILE / 2; idx += 256) {
+        int r = idx >> 6, c = (idx & 63) * 2;
+        double2 v;
+        v.x = S[r * DIAG_LD + c];
+        v.y = S[r * DIAG_LD + c + 1];
+        *reinterpret_cast<double2*>(D + r * CGP_TILE + c) = v;
+        double2 u;
+        u.x = S[c * DIAG_LD + r];
+        u.y = S[(c + 1) * DIAG_LD + r];
+        *reinterpret_cast<double2*>(Ut + (long long)r * ld + c) = u;
     }
 }
 

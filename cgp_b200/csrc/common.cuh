@@ -7,6 +7,7 @@
 #define CGP_TILE 128          // square tile edge of every blocked algorithm (padding granularity)
 #define CGP_BK 16             // k-chunk staged per pipeline stage (fp64)
 #define CGP_STAGES 4          // cp.async ring depth
+#define CGP_PANEL 4           // block columns per panel of the hybrid left/right-looking schedules
 #define CGP_GEMM_THREADS 256  // 8 warps: 2 (M) x 4 (N), warp tile 64 x 32
 #define CGP_MAX_D 16          // max input dimension
 #define CGP_MAX_K 8           // max k of k-NN

@@ -98,7 +98,7 @@ __device__ __forceinline__ void gemm_mainloop(GemmAcc& acc, double* smem, const 
 }
 
 // ---- epilogues -------------------------------------------------------------------------------
-// C[row, col] (row-major, ldc) op= acc.   MODE 0: C = acc   1: C = -acc   2: C -= acc
+// C[row, col] (row-major, ldc) op= acc.   MODE 0: C = acc   1: C = -acc   2: C -= acc   3: C += acc
 template <int MODE>
 __device__ __forceinline__ void gemm_store(const GemmAcc& acc, double* __restrict__ C, long long ldc) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -116,10 +116,14 @@ __device__ __forceinline__ void gemm_store(const GemmAcc& acc, double* __restric
             } else if (MODE == 1) {
                 o.x = -acc.v[mt][nt][0];
                 o.y = -acc.v[mt][nt][1];
-            } else {
+            } else if (MODE == 2) {
                 o = *p;
                 o.x -= acc.v[mt][nt][0];
                 o.y -= acc.v[mt][nt][1];
+            } else {
+                o = *p;
+                o.x += acc.v[mt][nt][0];
+                o.y += acc.v[mt][nt][1];
             }
             *p = o;
         }
@@ -161,10 +165,17 @@ k_dgemm_nt(const double* __restrict__ A, const double* __restrict__ B, double* _
     gemm_store<0>(acc, C + (long long)blockIdx.y * CGP_TILE * N + (long long)blockIdx.x * CGP_TILE, N);
 }
 
-// Left-looking Cholesky, block column j (j >= 1):  A[i,j] -= sum_{k<j} L[i,k] L[j,k]^T  for i >= j.
-// grid (Tmax - j, n_mats)
+// ---- blocked Cholesky, hybrid schedule --------------------------------------------------------------
+// Block columns are grouped in panels of CGP_PANEL tiles.  Inside a panel the factorisation is left-looking
+// (k_potrf_update with a short K), after a panel every trailing tile receives ONE rank-(128*CGP_PANEL) update
+// (k_potrf_trail).  The long left-looking K loops of a pure left-looking schedule put up to 4096-deep tile
+// products on the critical path and leave whole waves almost empty; this schedule keeps the critical path at
+// <= 3 short tile products per column while the bulk of the flops runs in large, uniform launches.
+// The summation order of every tile is fixed by (n, CGP_PANEL) alone -> results do not depend on the batch.
+
+// Column update inside a panel:  A[i,j] -= sum_{k=kb}^{j-1} L[i,k] L[j,k]^T  for i >= j.   grid (Tmax - j, n_mats)
 __global__ void __launch_bounds__(CGP_GEMM_THREADS, 1)
-k_potrf_update(double* __restrict__ Abuf, const MatMeta* __restrict__ meta, int j) {
+k_potrf_update(double* __restrict__ Abuf, const MatMeta* __restrict__ meta, int j, int kb) {
     const MatMeta m = meta[blockIdx.y];
     const int T = m.npad / CGP_TILE;
     const int i = j + blockIdx.x;
@@ -173,8 +184,31 @@ k_potrf_update(double* __restrict__ Abuf, const MatMeta* __restrict__ meta, int 
     const long long ld = m.npad;
     GemmAcc acc;
     gemm_zero(acc);
-    gemm_mainloop(acc, gemm_smem, A + (long long)i * CGP_TILE * ld, ld, A + (long long)j * CGP_TILE * ld, ld, j * CGP_TILE);
+    gemm_mainloop(acc, gemm_smem, A + (long long)i * CGP_TILE * ld + (long long)kb * CGP_TILE, ld,
+                  A + (long long)j * CGP_TILE * ld + (long long)kb * CGP_TILE, ld, (j - kb) * CGP_TILE);
     gemm_store<2>(acc, A + (long long)i * CGP_TILE * ld + (long long)j * CGP_TILE, ld);
+}
+
+// Trailing update after panel [c0, c1):  A[i,k] -= sum_{c=c0}^{c1-1} L[i,c] L[k,c]^T  for c1 <= k <= i < T.
+// grid (Tt(Tt+1)/2 with Tt = Tmax - c1, n_mats)
+__global__ void __launch_bounds__(CGP_GEMM_THREADS, 1)
+k_potrf_trail(double* __restrict__ Abuf, const MatMeta* __restrict__ meta, int c0, int c1) {
+    const MatMeta m = meta[blockIdx.y];
+    const int T = m.npad / CGP_TILE;
+    int idx = blockIdx.x, a = 0;
+    while (idx > a) {
+        idx -= a + 1;
+        ++a;
+    }
+    const int i = c1 + a, k = c1 + idx;
+    if (i >= T) return;
+    double* A = Abuf + m.a_off;
+    const long long ld = m.npad;
+    GemmAcc acc;
+    gemm_zero(acc);
+    gemm_mainloop(acc, gemm_smem, A + (long long)i * CGP_TILE * ld + (long long)c0 * CGP_TILE, ld,
+                  A + (long long)k * CGP_TILE * ld + (long long)c0 * CGP_TILE, ld, (c1 - c0) * CGP_TILE);
+    gemm_store<2>(acc, A + (long long)i * CGP_TILE * ld + (long long)k * CGP_TILE, ld);
 }
 
 // Panel: L[i,j] = A[i,j] * inv(L[j,j])^T for i > j  (triangular solve recast as a GEMM with the
@@ -194,24 +228,58 @@ k_potrf_panel(double* __restrict__ Abuf, const double* __restrict__ Dbuf, const 
     gemm_store<0>(acc, tile, ld);
 }
 
-// Triangular inverse, stored transposed: U = L^-T (upper, row-major).  Block column i (i >= 1):
-//   S[j,i] = sum_{k=j}^{i-1} U[j,k] L[i,k]^T   for j < i        (this kernel, written to U[j,i])
-//   U[j,i] = -S[j,i] * D_i^T                                     (k_trtri_scale)
-// grid (i, n_mats); heavy tiles (small j) first.
+// ---- triangular inverse, stored transposed: U = L^-T (upper, row-major), same hybrid schedule ------------
+//   U[j,i] = -( sum_{k=j}^{i-1} U[j,k] L[i,k]^T ) D_i^T   for j < i,   U[i,i] = D_i^T.
+// The sum over k is accumulated in place in the U[j,i] tile: contributions of a finished panel [c0, c1) are
+// pushed to every later column (k_trtri_trail), the columns of the current panel add their short inner part
+// (k_trtri_acc), then the tile is scaled by -D_i^T (k_trtri_scale).  The first contribution of a tile (the one
+// containing k = j) stores, later ones accumulate.
+
+// inner part of column i of panel [c0, ..):  rows j < i, k from max(j, c0) to i-1.   grid (i, n_mats)
 __global__ void __launch_bounds__(CGP_GEMM_THREADS, 1)
-k_trtri_acc(const double* __restrict__ Abuf, double* __restrict__ Ubuf, const MatMeta* __restrict__ meta, int i) {
+k_trtri_acc(const double* __restrict__ Abuf, double* __restrict__ Ubuf, const MatMeta* __restrict__ meta, int i, int c0) {
     const MatMeta m = meta[blockIdx.y];
     const int T = m.npad / CGP_TILE;
     const int j = blockIdx.x;
-    if (i >= T || j >= i) return;
+    const int kb = max(j, c0);
+    if (i >= T || j >= i || kb >= i) return;
     const long long ld = m.npad;
     const double* L = Abuf + m.a_off;
     double* U = Ubuf + m.u_off;
     GemmAcc acc;
     gemm_zero(acc);
-    gemm_mainloop(acc, gemm_smem, U + (long long)j * CGP_TILE * ld + (long long)j * CGP_TILE, ld,
-                  L + (long long)i * CGP_TILE * ld + (long long)j * CGP_TILE, ld, (i - j) * CGP_TILE);
-    gemm_store<0>(acc, U + (long long)j * CGP_TILE * ld + (long long)i * CGP_TILE, ld);
+    gemm_mainloop(acc, gemm_smem, U + (long long)j * CGP_TILE * ld + (long long)kb * CGP_TILE, ld,
+                  L + (long long)i * CGP_TILE * ld + (long long)kb * CGP_TILE, ld, (i - kb) * CGP_TILE);
+    double* out = U + (long long)j * CGP_TILE * ld + (long long)i * CGP_TILE;
+    if (j >= c0)
+        gemm_store<0>(acc, out, ld);
+    else
+        gemm_store<3>(acc, out, ld);
+}
+
+// push of the finished panel [c0, c1) into every later column i >= c1, rows j < c1.
+// grid (c1 * (Tmax - c1), n_mats): blockIdx.x = j * (Tmax - c1) + (i - c1)
+__global__ void __launch_bounds__(CGP_GEMM_THREADS, 1)
+k_trtri_trail(const double* __restrict__ Abuf, double* __restrict__ Ubuf, const MatMeta* __restrict__ meta, int c0, int c1,
+              int Tmax) {
+    const MatMeta m = meta[blockIdx.y];
+    const int T = m.npad / CGP_TILE;
+    const int w = Tmax - c1;
+    const int j = blockIdx.x / w, i = c1 + blockIdx.x % w;
+    if (i >= T) return;
+    const int kb = max(j, c0);
+    const long long ld = m.npad;
+    const double* L = Abuf + m.a_off;
+    double* U = Ubuf + m.u_off;
+    GemmAcc acc;
+    gemm_zero(acc);
+    gemm_mainloop(acc, gemm_smem, U + (long long)j * CGP_TILE * ld + (long long)kb * CGP_TILE, ld,
+                  L + (long long)i * CGP_TILE * ld + (long long)kb * CGP_TILE, ld, (c1 - kb) * CGP_TILE);
+    double* out = U + (long long)j * CGP_TILE * ld + (long long)i * CGP_TILE;
+    if (j >= c0)
+        gemm_store<0>(acc, out, ld);
+    else
+        gemm_store<3>(acc, out, ld);
 }
 
 __global__ void __launch_bounds__(CGP_GEMM_THREADS, 1)

@@ -160,7 +160,8 @@ class ClusterGPEngine:
         best = np.argmin(self.run_values, axis=1)  # first minimum in run order, SK/_gpr.py:336-337
         self.theta = np.stack([self.run_thetas[c, best[c]] for c in range(C)])
         self.fit_stats = dict(lockstep=steps, evals=int(n_eval[0]), nfev=nfev, nit=nit, pairs_local=len(mine),
-                              pairs_total=n_pairs)
+                              pairs_total=n_pairs,
+                              evals_per_cluster=np.bincount(pc_all, weights=nfev, minlength=C).astype(np.int64))
         self._factorize()
         return self
 
