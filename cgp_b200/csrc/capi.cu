@@ -277,7 +277,7 @@ static int run_pipeline(HandleImpl* h, int kind, const double* X, const double* 
         if (c1 < T)
             KL(h, CLS_TRTRI_TRAIL, s, k_trtri_trail<<<dim3(c1 * (T - c1), nm), CGP_GEMM_THREADS, GEMM_SMEM_BYTES, s>>>(b.A, b.U, b.meta, c0, c1, T));
     }
-    KL(h, CLS_SOLVE, s, k_solve_z<<<dim3(T, nm), 128, 0, s>>>(b.U, y, b.z, b.meta, b.npad_max));
+    KL(h, CLS_SOLVE, s, k_solve_z<<<dim3(T, nm), 1024, 0, s>>>(b.U, y, b.z, b.meta, b.npad_max));
     KL(h, CLS_SOLVE, s, k_solve_a<<<dim3(b.npad_max / 8, nm), 256, 0, s>>>(b.U, b.z, b.a, b.meta, b.npad_max));
     KL(h, CLS_SOLVE, s, k_lml_finish<<<nm, 256, 0, s>>>(b.z, b.logdet, info, lml, b.meta, b.npad_max, T));
     if (grad) {

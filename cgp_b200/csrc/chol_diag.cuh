@@ -17,6 +17,105 @@
 
 extern __shared__ __align__(16) double diag_smem[];
 
+// The three serial 32-wide routines below are written as template recursions instead of runtime loops so that
+// every index of the per-thread arrays is a compile-time constant: the arrays stay in registers and the
+// shared-memory operands (broadcast reads at static offsets) are hoisted out of the dependent FMA chains.
+
+// (1) one column step of the in-register 32x32 Cholesky (lane = row)
+template <int C>
+struct FactorCol {
+    static __device__ __forceinline__ void run(double (&row)[32], int lane, int& failcol, double& dinv) {
+        const double dcc = __shfl_sync(0xffffffffu, row[C], C);
+        if (!(dcc > 0.0) && failcol < 0) failcol = C;
+        const double ip = rsqrt(dcc);
+        const double lc = (lane == C) ? dcc * ip : row[C] * ip;
+        row[C] = lc;
+        if (lane == C) dinv = ip;
+#pragma unroll
+        for (int q = C + 1; q < 32; ++q) {
+            const double lq = __shfl_sync(0xffffffffu, lc, q);
+            if (lane >= q) row[q] -= lc * lq;
+        }
+        FactorCol<C + 1>::run(row, lane, failcol, dinv);
+    }
+};
+template <>
+struct FactorCol<32> {
+    static __device__ __forceinline__ void run(double (&)[32], int, int&, double&) {}
+};
+
+// (2) forward substitution of one row against the 32x32 factor Lp (row stride DIAG_LD): x <- x Lp^-T
+template <int C>
+struct PanelCol {
+    static __device__ __forceinline__ void run(double (&x)[32], const double* __restrict__ Lp, const double* __restrict__ rinv) {
+        double s0 = x[C], s1 = 0.0;
+#pragma unroll
+        for (int q = 0; q < C; ++q) {
+            if (q & 1)
+                s1 -= x[q] * Lp[C * DIAG_LD + q];
+            else
+                s0 -= x[q] * Lp[C * DIAG_LD + q];
+        }
+        x[C] = (s0 + s1) * rinv[C];
+        PanelCol<C + 1>::run(x, Lp, rinv);
+    }
+};
+template <>
+struct PanelCol<32> {
+    static __device__ __forceinline__ void run(double (&)[32], const double*, const double*) {}
+};
+
+// (3) column `lane` of the inverse of the 32x32 factor Lp: x_i = (delta_{i,lane} - sum_{k<i} Lp[i][k] x_k) / Lp[i][i]
+template <int I>
+struct InvRow {
+    static __device__ __forceinline__ void run(double (&x)[32], const double* __restrict__ Lp, const double* __restrict__ rinv, int lane) {
+        double s0 = (I == lane) ? 1.0 : 0.0, s1 = 0.0;
+#pragma unroll
+        for (int k = 0; k < I; ++k) {
+            if (k & 1)
+                s1 -= Lp[I * DIAG_LD + k] * x[k];
+            else
+                s0 -= Lp[I * DIAG_LD + k] * x[k];
+        }
+        x[I] = (s0 + s1) * rinv[I];
+        InvRow<I + 1>::run(x, Lp, rinv, lane);
+    }
+};
+template <>
+struct InvRow<32> {
+    static __device__ __forceinline__ void run(double (&)[32], const double*, const double*, int) {}
+};
+
+// rank-32 update of the trailing block of order 16*MB that starts at row/col t0, from the panel columns [k0, k0+32).
+// 16x16 thread grid, thread (ty, tx) owns rows ty + 16 i, cols tx + 16 j: row reads are 2-address broadcasts, column
+// reads walk 16 consecutive rows (stride 129 doubles) -> no bank conflicts.  Only 16x16 blocks with i >= j are touched.
+template <int MB>
+__device__ __forceinline__ void trail_update(double* __restrict__ S, int t0, int k0, int tid) {
+    const int ty = tid >> 4, tx = tid & 15;
+    double acc[MB][MB];
+#pragma unroll
+    for (int i = 0; i < MB; ++i)
+#pragma unroll
+        for (int jj = 0; jj < MB; ++jj) acc[i][jj] = 0.0;
+#pragma unroll 2
+    for (int c = 0; c < 32; ++c) {
+        double ra[MB], rb[MB];
+#pragma unroll
+        for (int i = 0; i < MB; ++i) {
+            ra[i] = S[(t0 + ty + 16 * i) * DIAG_LD + k0 + c];
+            rb[i] = S[(t0 + tx + 16 * i) * DIAG_LD + k0 + c];
+        }
+#pragma unroll
+        for (int i = 0; i < MB; ++i)
+#pragma unroll
+            for (int jj = 0; jj <= i; ++jj) acc[i][jj] += ra[i] * rb[jj];
+    }
+#pragma unroll
+    for (int i = 0; i < MB; ++i)
+#pragma unroll
+        for (int jj = 0; jj <= i; ++jj) S[(t0 + ty + 16 * i) * DIAG_LD + t0 + tx + 16 * jj] -= acc[i][jj];
+}
+
 // grid (n_mats), block 256.  logdet_part [n_mats][Tmax], info [n_out]
 __global__ void __launch_bounds__(256, 1)
 k_potrf_diag(double* __restrict__ Abuf, double* __restrict__ Ubuf, double* __restrict__ Dbuf,
@@ -32,15 +131,15 @@ k_potrf_diag(double* __restrict__ Abuf, double* __restrict__ Ubuf, double* __res
     double* tile = Abuf + m.a_off + (long long)j * CGP_TILE * ld + (long long)j * CGP_TILE;
     __shared__ int fail;
     if (tid == 0) fail = 0;
-    for (int idx = tid; idx < CGP_TILE * CGP_TILE / 2; idx += 256) {
-        int r = idx >> 6, c = (idx & 63) * 2;
-        double2 v = *reinterpret_cast<const double2*>(tile + (long long)r * ld + c);
-        S[r * DIAG_LD + c] = v.x;
-        S[r * DIAG_LD + c + 1] = v.y;
+#pragma unroll 8
+    for (int idx = tid; idx < CGP_TILE * CGP_TILE; idx += 256) {
+        int r = idx >> 7, c = idx & 127;
+        S[r * DIAG_LD + c] = tile[(long long)r * ld + c];
     }
     __syncthreads();
 
     // ---------------- potrf, blocked by 32
+#pragma unroll 1
     for (int k0 = 0; k0 < CGP_TILE; k0 += 32) {
         if (warp == 0) {
             double row[32];
@@ -48,87 +147,38 @@ k_potrf_diag(double* __restrict__ Abuf, double* __restrict__ Ubuf, double* __res
             for (int q = 0; q < 32; ++q) row[q] = (q <= lane) ? S[(k0 + lane) * DIAG_LD + k0 + q] : 0.0;
             int failcol = -1;
             double dinv = 0.0;
+            FactorCol<0>::run(row, lane, failcol, dinv);
 #pragma unroll
-            for (int c = 0; c < 32; ++c) {
-                const double dcc = __shfl_sync(0xffffffffu, row[c], c);
-                if (!(dcc > 0.0) && failcol < 0) failcol = c;
-                const double ip = rsqrt(dcc);
-                const double lc = (lane == c) ? dcc * ip : row[c] * ip;
-                row[c] = lc;
-                if (lane == c) dinv = ip;
-#pragma unroll
-                for (int q = c + 1; q < 32; ++q) {
-                    const double lq = __shfl_sync(0xffffffffu, lc, q);
-                    if (lane >= q) row[q] -= lc * lq;
-                }
-            }
-#pragma unroll
-            for (int q = 0; q < 32; ++q)
-                if (q <= lane) S[(k0 + lane) * DIAG_LD + k0 + q] = row[q];
+            for (int q = 0; q < 32; ++q) S[(k0 + lane) * DIAG_LD + k0 + q] = (q <= lane) ? row[q] : 0.0;
             rinv[k0 + lane] = dinv;
             if (lane == 0 && failcol >= 0 && fail == 0) fail = k0 + failcol + 1;
         }
         __syncthreads();
         const int mrem = CGP_TILE - k0 - 32;
-        if (tid < mrem) {  // sub-panel: rows below the diagonal piece, forward substitution
-            const int r = k0 + 32 + tid;
+        if (tid < mrem) {  // sub-panel below the diagonal piece: one thread per row
+            double* xr = S + (k0 + 32 + tid) * DIAG_LD + k0;
             double x[32];
 #pragma unroll
-            for (int c = 0; c < 32; ++c) {
-                double sacc = S[r * DIAG_LD + k0 + c];
+            for (int c = 0; c < 32; ++c) x[c] = xr[c];
+            PanelCol<0>::run(x, S + k0 * DIAG_LD + k0, rinv + k0);
 #pragma unroll
-                for (int q = 0; q < c; ++q) sacc -= x[q] * S[(k0 + c) * DIAG_LD + k0 + q];
-                x[c] = sacc * rinv[k0 + c];
-            }
-#pragma unroll
-            for (int c = 0; c < 32; ++c) S[r * DIAG_LD + k0 + c] = x[c];
+            for (int c = 0; c < 32; ++c) xr[c] = x[c];
         }
         __syncthreads();
-        const int nsub = mrem / 4, cnt = nsub * (nsub + 1) / 2;
-        for (int st = tid; st < cnt; st += 256) {  // rank-32 update of the trailing lower part, 4x4 register tiles
-            int a = (int)((sqrtf(8.0f * (float)st + 1.0f) - 1.0f) * 0.5f);
-            while (a * (a + 1) / 2 > st) --a;
-            while ((a + 1) * (a + 2) / 2 <= st) ++a;
-            const int b = st - a * (a + 1) / 2;
-            const int r0 = k0 + 32 + 4 * a, q0 = k0 + 32 + 4 * b;
-            double acc[4][4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int jj = 0; jj < 4; ++jj) acc[i][jj] = 0.0;
-#pragma unroll 4
-            for (int c = 0; c < 32; ++c) {
-                double ra[4], rb[4];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    ra[i] = S[(r0 + i) * DIAG_LD + k0 + c];
-                    rb[i] = S[(q0 + i) * DIAG_LD + k0 + c];
-                }
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-#pragma unroll
-                    for (int jj = 0; jj < 4; ++jj) acc[i][jj] += ra[i] * rb[jj];
-            }
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int jj = 0; jj < 4; ++jj) S[(r0 + i) * DIAG_LD + q0 + jj] -= acc[i][jj];
-        }
+        if (mrem == 96)
+            trail_update<6>(S, k0 + 32, k0, tid);
+        else if (mrem == 64)
+            trail_update<4>(S, k0 + 32, k0, tid);
+        else if (mrem == 32)
+            trail_update<2>(S, k0 + 32, k0, tid);
         __syncthreads();
     }
 
-    // ---------------- zero the strict upper part, write L_jj, log-determinant partial, status
+    // ---------------- write L_jj (strict upper zeroed), log-determinant partial, status
+#pragma unroll 8
     for (int idx = tid; idx < CGP_TILE * CGP_TILE; idx += 256) {
         int r = idx >> 7, c = idx & 127;
-        if (c > r) S[r * DIAG_LD + c] = 0.0;
-    }
-    __syncthreads();
-    for (int idx = tid; idx < CGP_TILE * CGP_TILE / 2; idx += 256) {
-        int r = idx >> 6, c = (idx & 63) * 2;
-        double2 v;
-        v.x = S[r * DIAG_LD + c];
-        v.y = S[r * DIAG_LD + c + 1];
-        *reinterpret_cast<double2*>(tile + (long long)r * ld + c) = v;
+        tile[(long long)r * ld + c] = (c <= r) ? S[r * DIAG_LD + c] : 0.0;
     }
     if (tid < 32) {
         double sl = 0.0;
@@ -143,22 +193,17 @@ k_potrf_diag(double* __restrict__ Abuf, double* __restrict__ Ubuf, double* __res
     __syncthreads();
 
     // ---------------- trtri (lower, in place), blocked by 32
-    if (warp < 4) {  // the four diagonal pieces: lane = column, forward substitution against e_lane
+    if (warp < 4) {  // the four diagonal pieces (their strict upper parts were zeroed above): lane = column
         const int k0 = warp * 32;
         double x[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-            double sacc = (i == lane) ? 1.0 : 0.0;
-#pragma unroll
-            for (int k = 0; k < i; ++k) sacc -= S[(k0 + i) * DIAG_LD + k0 + k] * x[k];
-            x[i] = sacc * rinv[k0 + i];
-        }
+        InvRow<0>::run(x, S + k0 * DIAG_LD + k0, rinv + k0, lane);
         __syncwarp();
 #pragma unroll
         for (int i = 0; i < 32; ++i)
             if (i >= lane) S[(k0 + i) * DIAG_LD + k0 + lane] = x[i];
     }
     __syncthreads();
+#pragma unroll 1
     for (int b = 2; b >= 0; --b) {
         // phase 1: T[a,b] = sum_{a'=b+1}^{a} W[a,a'] L[a',b]   for a = b+1..3  (W trailing part already inverted)
         const int blk = tid >> 6, sub = tid & 63;
@@ -177,8 +222,8 @@ k_potrf_diag(double* __restrict__ Abuf, double* __restrict__ Ubuf, double* __res
                     double wa[4], lb[4];
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
-                        wa[i] = S[(32 * a + 4 * ti + i) * DIAG_LD + 32 * ap + k];
-                        lb[i] = S[(32 * ap + k) * DIAG_LD + 32 * b + 4 * tj + i];
+                        wa[i] = S[(32 * a + ti + 8 * i) * DIAG_LD + 32 * ap + k];
+                        lb[i] = S[(32 * ap + k) * DIAG_LD + 32 * b + tj + 8 * i];
                     }
 #pragma unroll
                     for (int i = 0; i < 4; ++i)
@@ -192,7 +237,7 @@ k_potrf_diag(double* __restrict__ Abuf, double* __restrict__ Ubuf, double* __res
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
-                for (int jj = 0; jj < 4; ++jj) S[(32 * a + 4 * ti + i) * DIAG_LD + 32 * b + 4 * tj + jj] = acc[i][jj];
+                for (int jj = 0; jj < 4; ++jj) S[(32 * a + ti + 8 * i) * DIAG_LD + 32 * b + tj + 8 * jj] = acc[i][jj];
         }
         __syncthreads();
         // phase 2: W[a,b] = -T[a,b] W[b,b]
@@ -206,8 +251,8 @@ k_potrf_diag(double* __restrict__ Abuf, double* __restrict__ Ubuf, double* __res
                 double ta[4], wb[4];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    ta[i] = S[(32 * a + 4 * ti + i) * DIAG_LD + 32 * b + k];
-                    wb[i] = S[(32 * b + k) * DIAG_LD + 32 * b + 4 * tj + i];
+                    ta[i] = S[(32 * a + ti + 8 * i) * DIAG_LD + 32 * b + k];
+                    wb[i] = S[(32 * b + k) * DIAG_LD + 32 * b + tj + 8 * i];
                 }
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
@@ -220,41 +265,48 @@ k_potrf_diag(double* __restrict__ Abuf, double* __restrict__ Ubuf, double* __res
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
-                for (int jj = 0; jj < 4; ++jj) S[(32 * a + 4 * ti + i) * DIAG_LD + 32 * b + 4 * tj + jj] = -acc[i][jj];
+                for (int jj = 0; jj < 4; ++jj) S[(32 * a + ti + 8 * i) * DIAG_LD + 32 * b + tj + 8 * jj] = -acc[i][jj];
         }
         __syncthreads();
     }
 
+    // D_j = inverse (row-major lower), U_jj = D_j^T.  Only the lower part of S is meaningful here.
     double* D = Dbuf + m.d_off + (long long)j * CGP_TILE * CGP_TILE;
     double* Ut = Ubuf + m.u_off + (long long)j * CGP_TILE * ld + (long long)j * CGP_TILE;
-    for (int idx = tid; idx < CGP_TILE * CGP_TILE / 2; idx += 256) {
-        int r = idx >> 6, c = (idx & 63) * 2;
-        double2 v;
-        v.x = S[r * DIAG_LD + c];
-        v.y = S[r * DIAG_LD + c + 1];
-        *reinterpret_cast<double2*>(D + r * CGP_TILE + c) = v;
-        double2 u;
-        u.x = S[c * DIAG_LD + r];
-        u.y = S[(c + 1) * DIAG_LD + r];
-        *reinterpret_cast<double2*>(Ut + (long long)r * ld + c) = u;
+#pragma unroll 8
+    for (int idx = tid; idx < CGP_TILE * CGP_TILE; idx += 256) {
+        int r = idx >> 7, c = idx & 127;
+        D[r * CGP_TILE + c] = (c <= r) ? S[r * DIAG_LD + c] : 0.0;
+        Ut[(long long)r * ld + c] = (c >= r) ? S[c * DIAG_LD + r] : 0.0;
     }
 }
 
 // ---- y solves and the LML value ----------------------------------------------------------------
-// z = L^-1 y = U^T y :  z_i = sum_{k<=i} U[k,i] y_k.   grid (Tmax, n_mats), block 128 (thread = column)
-__global__ void __launch_bounds__(128)
+// z = L^-1 y = U^T y :  z_i = sum_{k<=i} U[k,i] y_k.   grid (Tmax, n_mats), block 1024:
+// thread (g = tid>>7, c = tid&127) sums rows k = g, g+8, ... of column c; the 8 partials are added in fixed order.
+__global__ void __launch_bounds__(1024)
 k_solve_z(const double* __restrict__ Ubuf, const double* __restrict__ y, double* __restrict__ zbuf,
           const MatMeta* __restrict__ meta, int zstride) {
     const MatMeta m = meta[blockIdx.y];
-    const int i = blockIdx.x * CGP_TILE + threadIdx.x;
-    if (i >= m.npad) return;
+    __shared__ double part[8][CGP_TILE];
+    const int c = threadIdx.x & 127, g = threadIdx.x >> 7;
+    const int i = blockIdx.x * CGP_TILE + c;
+    if (blockIdx.x * CGP_TILE >= m.npad) return;
     const double* U = Ubuf + m.u_off;
     const long long ld = m.npad;
     const double* yy = y + m.xoff;
     double s = 0.0;
     const int kend = min(i, m.n - 1);
-    for (int k = 0; k <= kend; ++k) s += U[(long long)k * ld + i] * yy[k];
-    zbuf[(long long)blockIdx.y * zstride + i] = (i < m.n) ? s : 0.0;
+#pragma unroll 4
+    for (int k = g; k <= kend; k += 8) s += U[(long long)k * ld + i] * yy[k];
+    part[g][c] = s;
+    __syncthreads();
+    if (g == 0) {
+        double t = 0.0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) t += part[q][c];
+        zbuf[(long long)blockIdx.y * zstride + i] = (i < m.n) ? t : 0.0;
+    }
 }
 
 // a = L^-T z = U z :  a_j = sum_{k>=j} U[j,k] z_k.   warp per row; grid (npad_max/8, n_mats), block 256

@@ -158,7 +158,7 @@ k_grad_tiles(const double* __restrict__ Kinv, const double* __restrict__ X, cons
     for (int p = 0; p < DMAX; ++p) {
         G[p] = 0.0;
         double l = (p < d) ? exp(th[p]) : 1.0;
-        il2[p] = l * l;
+        il2[p] = 1.0 / (l * l);
         xc[p] = (p < d) ? xj[c * sd + p] : 0.0;
     }
     const double* Kt = Kinv + m.a_off;
@@ -174,7 +174,7 @@ k_grad_tiles(const double* __restrict__ Kinv, const double* __restrict__ X, cons
 #pragma unroll
             for (int p = 0; p < DMAX; ++p) {
                 double t = (p < d) ? xi[r * sd + p] - xc[p] : 0.0;
-                Dp[p] = (t * t) / il2[p];
+                Dp[p] = (t * t) * il2[p];
                 s += Dp[p];
             }
             double e;

@@ -63,7 +63,7 @@ def main():
     labels = np.empty(n, dtype=np.int64)
     labels[order] = np.repeat(np.arange(Cn), nc)
     eng = ClusterGPEngine(X, yv, labels, "matern32", 1e-5)
-    for B in ([4] if quick else [8, 17 * 8]):
+    for B in ([1, 4] if quick else [1, 8, 17 * 8]):
         pc = np.arange(B, dtype=np.int32) % Cn
         th = rng.uniform(-1.5, 0.5, size=(B, d + 1))
         th[:, d] = rng.uniform(-6, -2, size=B)
@@ -72,7 +72,13 @@ def main():
         torch.cuda.synchronize()
         t, tm = timeit(lambda: eng.lml_grad(pc, th, True), warm=1, rep=3)
         flops = B * float(nc) ** 3  # n^3/3 potrf + n^3/3 trtri + n^3/3 lauum
-        out[f"lml_grad_B{B}_n{nc}"] = {"s": t, "tflops_alg": flops / t / 1e12, "first_call_s": time.perf_counter() - t0}
+        _lib.profile_read(reset=True)
+        _lib.profile_enable(True)
+        eng.lml_grad(pc, th, True)
+        prof = {k: round(v[0], 3) for k, v in _lib.profile_read(reset=True).items() if v[1]}
+        _lib.profile_enable(False)
+        out[f"lml_grad_B{B}_n{nc}"] = {"s": t, "tflops_alg": flops / t / 1e12, "first_call_s": time.perf_counter() - t0,
+                                       "class_ms": prof}
     th = np.tile(np.array([-0.7] * d + [-4.0]), (Cn, 1))
     eng.set_theta(th)
     t, _ = timeit(lambda: eng._factorize(), warm=1, rep=3)
