@@ -23,6 +23,19 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """Print the ONE JSON line on the real stdout (library chatter such as NCCL's version banner is routed to stderr)."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 METRIC = "cGP fit+acq iteration (n=32k, 8 clusters, 16 restarts, 4M EI candidates): EI candidates/sec"
 UNIT = "candidates/s"
 # Total LML+grad evaluations of one config-3 fit (8 clusters x 17 L-BFGS-B runs), measured by the B200 arm
@@ -179,7 +192,7 @@ def run_reference(args, p):
             "config": {"workload": p["name"], "timing": "host wall clock of a bounded sample, extrapolated (see cpu_baseline.sample)"},
             "cpu_baseline": last,
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------ B200 arm
@@ -337,7 +350,7 @@ def run_b200(args, p):
                     "d2h_bytes_per_step": int((p["d"] + 2) * 8), "ms_per_step": e2e_s * 1e3},
             "gpu_launches": gpu_launches, "kernel_ms_timed_region": kernel_ms,
             "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks}
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -352,6 +365,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     p = PRESETS[args.preset]
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args, p)
     else:

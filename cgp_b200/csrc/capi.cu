@@ -480,6 +480,7 @@ extern "C" int cgp_factorize(cgp_handle* hh, int kind, const double* X, const do
     CGP_CHECK(cudaMemsetAsync(info, 0, (size_t)C * sizeof(int32_t), s));
     int64_t elems = cgp_model_elems(offs, C);
     CGP_CHECK(cudaMemsetAsync(b.U, 0, (size_t)elems * 8, s));
+    CGP_CHECK(cudaMemsetAsync(L, 0, (size_t)elems * 8, s));  // strictly-upper tiles are never written by the pipeline
     int rc = upload(h, b.meta, metas.data(), (size_t)C * sizeof(MatMeta), s);
     if (rc) return rc;
     rc = run_pipeline(h, kind, X, y, theta, alpha, d, b, lml, nullptr, info, s);

@@ -5,8 +5,12 @@
 #include <math.h>
 
 #define CGP_TILE 128          // square tile edge of every blocked algorithm (padding granularity)
-#define CGP_BK 16             // k-chunk staged per pipeline stage (fp64)
-#define CGP_STAGES 4          // cp.async ring depth
+#ifndef CGP_BK
+#define CGP_BK 32             // k-chunk staged per pipeline stage (fp64)
+#endif
+#ifndef CGP_STAGES
+#define CGP_STAGES 3          // cp.async ring depth (3 x 64 KB)
+#endif
 #define CGP_PANEL 4           // block columns per panel of the hybrid left/right-looking schedules
 #define CGP_GEMM_THREADS 256  // 8 warps: 2 (M) x 4 (N), warp tile 64 x 32
 #define CGP_MAX_D 16          // max input dimension

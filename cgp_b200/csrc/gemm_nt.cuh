@@ -18,10 +18,11 @@ __device__ __forceinline__ int gemm_swz(int row, int chunk) { return chunk ^ ((r
 __device__ __forceinline__ void gemm_load_stage(double* sa, double* sb, const double* __restrict__ gA,
                                                 long long lda, const double* __restrict__ gB,
                                                 long long ldb, int k0, int tid) {
+    constexpr int CPR = CGP_BK / 2;  // 16-byte chunks per tile row
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < CGP_TILE * CPR / CGP_GEMM_THREADS; ++i) {
         int idx = tid + i * CGP_GEMM_THREADS;
-        int row = idx >> 3, c = idx & 7;
+        int row = idx / CPR, c = idx % CPR;
         int pc = gemm_swz(row, c) * 2;
         cp_async16(sa + row * CGP_BK + pc, gA + (long long)row * lda + k0 + c * 2);
         cp_async16(sb + row * CGP_BK + pc, gB + (long long)row * ldb + k0 + c * 2);
@@ -71,7 +72,7 @@ __device__ __forceinline__ void gemm_mainloop(GemmAcc& acc, double* smem, const 
         const double* a_s = sA + (kt % CGP_STAGES) * GEMM_TILE_ELEMS;
         const double* b_s = sB + (kt % CGP_STAGES) * GEMM_TILE_ELEMS;
 #pragma unroll
-        for (int kk = 0; kk < 2; ++kk) {
+        for (int kk = 0; kk < CGP_BK / 8; ++kk) {
             double2 af[8], bf[4];
 #pragma unroll
             for (int mt = 0; mt < 8; ++mt) {

@@ -121,7 +121,7 @@ int cgp_ei_argmax(cgp_handle* h, int kind, const double* X, const int64_t* offs_
                   size_t workspace_bytes, void* stream);
 
 /* Measurement helper (bench / tests only): C[M,N] = A[M,K] * B[N,K]^T through the same fp64
- * tensor-core (DMMA) tile mainloop every factorisation step uses.  M,N multiples of 128, K of 16. */
+ * tensor-core (DMMA) tile mainloop every factorisation step uses.  M,N multiples of 128, K of 32. */
 int cgp_dgemm_nt(cgp_handle* h, const double* A, const double* B, double* C, int64_t M, int64_t N,
                  int64_t K, void* stream);
 

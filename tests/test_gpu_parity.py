@@ -29,7 +29,7 @@ def dev(a, dtype=torch.float64):
 
 
 # ------------------------------------------------------------------------------------------------ DMMA mainloop
-@pytest.mark.parametrize("M,N,K", [(128, 128, 16), (256, 384, 160), (512, 128, 2048)])
+@pytest.mark.parametrize("M,N,K", [(128, 128, 32), (256, 384, 160), (512, 128, 2048)])
 def test_dgemm_nt(lib, M, N, K):
     g = torch.Generator(device="cuda").manual_seed(1)
     A = torch.randn((M, K), dtype=torch.float64, device="cuda", generator=g)
