@@ -46,6 +46,10 @@ struct HandleImpl : cgp_handle {
     size_t recs_used;
     double ms[CLS_COUNT];
     long long launches[CLS_COUNT];
+    // second stream: the triangular-inverse chain of panel s runs beside the Cholesky chain of panel s+1
+    cudaStream_t s2;
+    std::vector<cudaEvent_t> panel_ev;
+    cudaEvent_t join_ev;
 };
 
 static inline void prof_begin(HandleImpl* h, int cls, cudaStream_t s) {
@@ -106,6 +110,12 @@ extern "C" int cgp_create(cgp_handle** out, int device) {
     h->ring_event_pending = false;
     h->prof_on = false;
     h->recs_used = 0;
+    {
+        int lo = 0, hi = 0;
+        CGP_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CGP_CHECK(cudaStreamCreateWithPriority(&h->s2, cudaStreamNonBlocking, lo));  // lowest priority: fills gaps
+        CGP_CHECK(cudaEventCreateWithFlags(&h->join_ev, cudaEventDisableTiming));
+    }
     for (int i = 0; i < CLS_COUNT; ++i) h->ms[i] = 0.0, h->launches[i] = 0;
     CGP_CHECK(set_smem(k_dgemm_nt, GEMM_SMEM_BYTES));
     CGP_CHECK(set_smem(k_potrf_update, GEMM_SMEM_BYTES));
@@ -128,6 +138,9 @@ extern "C" int cgp_destroy(cgp_handle* hh) {
         cudaEventDestroy(r.a);
         cudaEventDestroy(r.b);
     }
+    for (auto& e : h->panel_ev) cudaEventDestroy(e);
+    cudaEventDestroy(h->join_ev);
+    cudaStreamDestroy(h->s2);
     cudaEventDestroy(h->ring_event);
     cudaFreeHost(h->pinned);
     delete h;
@@ -253,7 +266,17 @@ static int run_pipeline(HandleImpl* h, int kind, const double* X, const double* 
         KL(h, CLS_ASSEMBLE, s, k_assemble<0><<<gl, 256, xs, s>>>(b.A, X, theta, b.meta, d, alpha));
     else
         KL(h, CLS_ASSEMBLE, s, k_assemble<1><<<gl, 256, xs, s>>>(b.A, X, theta, b.meta, d, alpha));
-    for (int c0 = 0; c0 < T; c0 += CGP_PANEL) {
+    // Cholesky chain on the caller's stream; the triangular-inverse work of panel p only needs the Cholesky panel p
+    // (not its trailing update), so it is issued on a second stream behind an event and overlaps panel p+1.
+    const int n_panels = (T + CGP_PANEL - 1) / CGP_PANEL;
+    const bool fork = n_panels > 1;
+    cudaStream_t st = fork ? h->s2 : s;
+    while ((int)h->panel_ev.size() < n_panels) {
+        cudaEvent_t e;
+        CGP_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        h->panel_ev.push_back(e);
+    }
+    for (int c0 = 0, p = 0; c0 < T; c0 += CGP_PANEL, ++p) {
         const int c1 = std::min(T, c0 + CGP_PANEL);
         for (int j = c0; j < c1; ++j) {
             if (j > c0)
@@ -262,20 +285,25 @@ static int run_pipeline(HandleImpl* h, int kind, const double* X, const double* 
             if (j + 1 < T)
                 KL(h, CLS_POTRF_PANEL, s, k_potrf_panel<<<dim3(T - j - 1, nm), CGP_GEMM_THREADS, GEMM_SMEM_BYTES, s>>>(b.A, b.D, b.meta, j));
         }
+        if (fork) {
+            CGP_CHECK(cudaEventRecord(h->panel_ev[p], s));
+            CGP_CHECK(cudaStreamWaitEvent(st, h->panel_ev[p], 0));
+        }
         if (c1 < T) {
             const int Tt = T - c1;
             KL(h, CLS_POTRF_TRAIL, s, k_potrf_trail<<<dim3(Tt * (Tt + 1) / 2, nm), CGP_GEMM_THREADS, GEMM_SMEM_BYTES, s>>>(b.A, b.meta, c0, c1));
         }
-    }
-    for (int c0 = 0; c0 < T; c0 += CGP_PANEL) {
-        const int c1 = std::min(T, c0 + CGP_PANEL);
         for (int i = std::max(c0, 1); i < c1; ++i) {
             if (i > c0)
-                KL(h, CLS_TRTRI_ACC, s, k_trtri_acc<<<dim3(i, nm), CGP_GEMM_THREADS, GEMM_SMEM_BYTES, s>>>(b.A, b.U, b.meta, i, c0));
-            KL(h, CLS_TRTRI_SCALE, s, k_trtri_scale<<<dim3(i, nm), CGP_GEMM_THREADS, GEMM_SMEM_BYTES, s>>>(b.U, b.D, b.meta, i));
+                KL(h, CLS_TRTRI_ACC, st, k_trtri_acc<<<dim3(i, nm), CGP_GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(b.A, b.U, b.meta, i, c0));
+            KL(h, CLS_TRTRI_SCALE, st, k_trtri_scale<<<dim3(i, nm), CGP_GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(b.U, b.D, b.meta, i));
         }
         if (c1 < T)
-            KL(h, CLS_TRTRI_TRAIL, s, k_trtri_trail<<<dim3(c1 * (T - c1), nm), CGP_GEMM_THREADS, GEMM_SMEM_BYTES, s>>>(b.A, b.U, b.meta, c0, c1, T));
+            KL(h, CLS_TRTRI_TRAIL, st, k_trtri_trail<<<dim3(c1 * (T - c1), nm), CGP_GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(b.A, b.U, b.meta, c0, c1, T));
+    }
+    if (fork) {
+        CGP_CHECK(cudaEventRecord(h->join_ev, st));
+        CGP_CHECK(cudaStreamWaitEvent(s, h->join_ev, 0));
     }
     KL(h, CLS_SOLVE, s, k_solve_z<<<dim3(T, nm), 1024, 0, s>>>(b.U, y, b.z, b.meta, b.npad_max));
     KL(h, CLS_SOLVE, s, k_solve_a<<<dim3(b.npad_max / 8, nm), 256, 0, s>>>(b.U, b.z, b.a, b.meta, b.npad_max));

@@ -132,10 +132,12 @@ k_potrf_diag(double* __restrict__ Abuf, double* __restrict__ Ubuf, double* __res
     __shared__ int fail;
     if (tid == 0) fail = 0;
 #pragma unroll 8
-    for (int idx = tid; idx < CGP_TILE * CGP_TILE; idx += 256) {
+    for (int idx = tid; idx < CGP_TILE * CGP_TILE; idx += 256) {  // 64 asynchronous 8-byte copies in flight per thread
         int r = idx >> 7, c = idx & 127;
-        S[r * DIAG_LD + c] = tile[(long long)r * ld + c];
+        cp_async8(S + r * DIAG_LD + c, tile + (long long)r * ld + c);
     }
+    cp_async_commit();
+    cp_async_wait<0>();
     __syncthreads();
 
     // ---------------- potrf, blocked by 32
