@@ -147,3 +147,32 @@ def test_shard_independence_and_edges():
     assert int(c.item()) == 0
     mean, std = eng.predict(Q[:0])
     assert mean.numel() == 0
+
+
+def test_config4_shape_single_large_cluster():
+    """configs[3] in miniature: ONE cluster whose matrix spans many panels of the blocked factorisation
+    (n = 5000 -> 40 tiles, 10 panels, ragged last tile), 4-D Matern-3/2.  LML + gradient vs the LAPACK oracle,
+    posterior mean/std vs the oracle on a candidate subset."""
+    from cgp_b200.engine import ClusterGPEngine
+
+    rng = np.random.default_rng(0)
+    n, d = 5000, 4
+    X = rng.uniform(size=(n, d))
+    y = np.sin(4 * np.pi * X[:, 0]) * np.cos(2 * np.pi * X[:, 1]) + X[:, 2] * X[:, 3] + 1e-2 * rng.standard_normal(n)
+    lab = np.zeros(n, dtype=np.int64)
+    eng = ClusterGPEngine(X, y, lab, "matern32", 1e-5)
+    th = np.array([-1.2, -0.9, 0.3, 0.1, -7.0])
+    lml, grad, info = eng.lml_grad([0], th[None, :], True)
+    yn, ym, ys = oracle.normalize_y(y)
+    l_ref, g_ref = oracle.lml_and_grad(X, yn, th, 1e-5, "matern32")
+    assert info[0] == 0
+    assert abs(lml[0] - l_ref) <= RTOL * abs(l_ref)
+    assert np.max(np.abs(grad[0] - g_ref)) <= 1e-6 * max(1.0, np.max(np.abs(g_ref)))
+    eng.set_theta(th[None, :])
+    Q = rng.uniform(size=(3000, d))
+    mean, std = eng.predict(Q)
+    models = _oracle_models(X, y, lab, th[None, :])
+    mu, sd = oracle.predict_mean_std(X, th, models[0]["L"], models[0]["alpha_vec"], ym, ys, Q)
+    assert relerr(mean.cpu().numpy(), mu) < 1e-7
+    ok = sd > 1e-3
+    assert relerr(std.cpu().numpy()[ok], sd[ok]) < 1e-6
