@@ -229,7 +229,7 @@ def run_b200(args, p):
         e[2].record()
         torch.cuda.synchronize()
         stats.update(fit_s=e[0].elapsed_time(e[1]) * 1e-3, acq_s=e[1].elapsed_time(e[2]) * 1e-3, evals=eng.fit_stats["evals"],
-                     lockstep=eng.fit_stats["lockstep"], evals_per_cluster=eng.fit_stats["evals_per_cluster"].tolist(), nfev_sorted=sorted(int(v) for v in eng.fit_stats["nfev"]), x_next=x_next.tolist(), score=score, idx=idx, cluster=cl,
+                     lockstep=eng.fit_stats["lockstep"], eval_s=eng.fit_stats["eval_s"], opt_host_s=eng.fit_stats["optimizer_host_s"], evals_per_cluster=eng.fit_stats["evals_per_cluster"].tolist(), nfev_sorted=sorted(int(v) for v in eng.fit_stats["nfev"]), x_next=x_next.tolist(), score=score, idx=idx, cluster=cl,
                      sizes=eng.counts.tolist(), lml=eng.model["lml_host"].tolist())
         return x_next
 
@@ -342,7 +342,7 @@ def run_b200(args, p):
                        "timing": "CUDA events around K whole steps, barrier+synchronize both sides, max over ranks"},
             "iteration_s": step_s, "fit_s": res["fit_s"], "acq_s": res["acq_s"],
             "acq_candidates_per_s": p["M"] / res["acq_s"], "lml_evals_per_fit_rank0": res["evals"],
-            "lockstep_per_fit": res["lockstep"], "nfev_per_pair_rank0_sorted": res["nfev_sorted"], "selected": {"idx": res["idx"], "score": res["score"], "cluster": res["cluster"],
+            "lockstep_per_fit": res["lockstep"], "fit_eval_wall_s": res["eval_s"], "fit_optimizer_host_s": res["opt_host_s"], "nfev_per_pair_rank0_sorted": res["nfev_sorted"], "selected": {"idx": res["idx"], "score": res["score"], "cluster": res["cluster"],
                                                               "x": res["x_next"]},
             "wall_s_per_step": t_wall / args.steps,
             "e2e": {"value": p["M"] / e2e_s, "unit": UNIT,

@@ -7,6 +7,7 @@ over ranks.  No CPU fallback.
 from __future__ import annotations
 
 import math
+import time
 
 import numpy as np
 import torch
@@ -146,13 +147,18 @@ class ClusterGPEngine:
         pc_all = np.asarray([p // R1 for p in mine], dtype=np.int32)
         x0s = [starts[p % R1] for p in mine]
         n_eval = [0]
+        t_eval = [0.0]
+        t_fit0 = time.perf_counter()
 
         def eval_batch(idx, Xs):
+            t0 = time.perf_counter()
             lml, grad, _ = self.lml_grad(pc_all[idx], Xs, True)
             n_eval[0] += len(idx)
+            t_eval[0] += time.perf_counter() - t0
             return -lml, -grad
 
         xs, fs, nfev, nit, steps = minimize_lockstep(eval_batch, x0s, lo, hi)
+        t_opt = time.perf_counter() - t_fit0
         rows = torch.from_numpy(np.concatenate([xs, fs[:, None]], axis=1).reshape(len(mine), P + 1)).to(self.device)
         table = cdist.gather_pair_rows(rows, n_pairs, rank, ws).cpu().numpy().reshape(C, R1, P + 1)
         self.run_thetas = table[:, :, :P]
@@ -160,7 +166,7 @@ class ClusterGPEngine:
         best = np.argmin(self.run_values, axis=1)  # first minimum in run order, SK/_gpr.py:336-337
         self.theta = np.stack([self.run_thetas[c, best[c]] for c in range(C)])
         self.fit_stats = dict(lockstep=steps, evals=int(n_eval[0]), nfev=nfev, nit=nit, pairs_local=len(mine),
-                              pairs_total=n_pairs,
+                              pairs_total=n_pairs, eval_s=t_eval[0], optimizer_host_s=t_opt - t_eval[0],
                               evals_per_cluster=np.bincount(pc_all, weights=nfev, minlength=C).astype(np.int64))
         self._factorize()
         return self
