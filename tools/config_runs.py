@@ -1,0 +1,116 @@
+"""Timings of the other BASELINE.json configs on ONE B200 (bench.py's headline is config 3).
+    python tools/config_runs.py cfg2 | cfg5 [--m M] | cfg4 [--n N --m M]
+Data definitions: SURVEY.md §8d."""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from cgp_b200 import _lib  # noqa: E402
+from cgp_b200.engine import ClusterGPEngine  # noqa: E402
+
+
+def sync_time(fn):
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    out = fn()
+    torch.cuda.synchronize()
+    return time.perf_counter() - t0, out
+
+
+def arg(name, default):
+    return type(default)(sys.argv[sys.argv.index(name) + 1]) if name in sys.argv else default
+
+
+def cfg2():
+    """Schaffer N2 2-D, N_PILOT=2000, DGM4 clusters (host), R=20, 64k candidates."""
+    import oracle
+    from cgp_b200.plugins import DGM4
+
+    np.random.seed(123)
+    N, d, M, R = 2000, 2, 65536, 20
+    X = np.zeros((N, d))
+    for j in range(d):
+        X[:, j] = np.random.uniform(-100, 100, size=(N, 1)).ravel()
+    x, yy = X[:, 0], X[:, 1]
+    y = 0.5 + (np.sin(x * x - yy * yy) ** 2 - 0.5) / (1 + 0.001 * (x * x + yy * yy)) ** 2
+    t_cl = time.perf_counter()
+    lab = DGM4.f_Cluster(123).fit_predict(np.concatenate([X, y[:, None]], axis=1))
+    lab = oracle.recode(oracle.merge_small_clusters(lab, d))
+    t_cl = time.perf_counter() - t_cl
+    Q = np.random.default_rng(2024).uniform(-100, 100, size=(M, d))
+    return X, y, lab, Q, R, dict(host_clustering_s=t_cl)
+
+
+def cfg5():
+    """8-D, 64 clusters of n_c in [480, 544] (cells of a 2^6 split on x0..x5), R=32, 16M candidates."""
+    rng = np.random.default_rng(0)
+    C, d, R = 64, 8, 32
+    M = arg("--m", 16777216)
+    sizes = rng.integers(480, 545, size=C)
+    Xs, labs = [], []
+    for c in range(C):
+        x = rng.uniform(size=(sizes[c], d))
+        for b in range(6):
+            x[:, b] = 0.5 * x[:, b] + 0.5 * ((c >> b) & 1)
+        Xs.append(x)
+        labs.append(np.full(sizes[c], c))
+    X, lab = np.concatenate(Xs), np.concatenate(labs)
+    perm = rng.permutation(X.shape[0])
+    X, lab = X[perm], lab[perm]
+    y = lab % 7 + np.sin(2 * np.pi * X.sum(1) / 8) + 0.01 * rng.standard_normal(X.shape[0])
+    Q = np.random.default_rng(1).uniform(size=(M, d))
+    return X, y, lab, Q, R, {}
+
+
+def run_fit_scan(name, X, y, lab, Q, R, extra):
+    out = dict(config=name, n=int(X.shape[0]), d=int(X.shape[1]), clusters=int(lab.max()) + 1, R=R, M=int(Q.shape[0]), **extra)
+    Qd = torch.from_numpy(Q).cuda()
+    for rep in range(2):  # second repetition is the warm one
+        eng = ClusterGPEngine(X, y, lab, "matern32", 1e-5)
+        t_fit, _ = sync_time(lambda: eng.fit(R, seed=0))
+        t_knn, ql = sync_time(lambda: eng.route(Qd, 3))
+        t_scan, res = sync_time(lambda: eng.ei_scan(Qd, 3, qlabel=ql))
+    out.update(fit_s=t_fit, evals=eng.fit_stats["evals"], lockstep=eng.fit_stats["lockstep"], knn_s=t_knn, scan_s=t_scan,
+               iteration_s=t_fit + t_knn + t_scan, cand_per_s_acq=Q.shape[0] / (t_knn + t_scan),
+               best=dict(score=float(res[0][0].item()), idx=int(res[0][1].item()), cluster=int(res[0][2].item())))
+    print(json.dumps(out))
+
+
+def cfg4():
+    """single cluster, 4-D Matern-3/2: blocked DMMA Cholesky stress (one LML+grad evaluation, final factorisation, scan)."""
+    n = arg("--n", 65536)
+    M = arg("--m", 1048576)
+    d = 4
+    rng = np.random.default_rng(0)
+    X = rng.uniform(size=(n, d))
+    y = np.sin(4 * np.pi * X[:, 0]) * np.cos(2 * np.pi * X[:, 1]) + X[:, 2] * X[:, 3] + 1e-2 * rng.standard_normal(n)
+    lab = np.zeros(n, dtype=np.int64)
+    eng = ClusterGPEngine(X, y, lab, "matern32", 1e-5, mem_fraction=0.9)
+    th = np.array([-1.2, -0.9, 0.3, 0.1, -7.0])
+    t_eval, (lml, grad, info) = sync_time(lambda: eng.lml_grad([0], th[None, :], True))
+    t_eval2, _ = sync_time(lambda: eng.lml_grad([0], th[None, :] + 0.01, True))
+    t_fac, _ = sync_time(lambda: eng.set_theta(th[None, :]))
+    Qd = torch.from_numpy(np.random.default_rng(1).uniform(size=(M, d))).cuda()
+    t_knn, ql = sync_time(lambda: eng.route(Qd, 3))
+    t_scan, res = sync_time(lambda: eng.ei_scan(Qd, 3, qlabel=ql))
+    fl = float(n) ** 3
+    print(json.dumps(dict(config="cfg4", n=n, d=d, M=M, lml=float(lml[0]), info=int(info[0]), grad=grad[0].tolist(),
+                          lml_grad_eval_s=t_eval2, first_eval_s=t_eval, tflops_alg=fl / t_eval2 / 1e12, factorize_s=t_fac,
+                          knn_s=t_knn, scan_s=t_scan, scan_tflops_alg=M * float(n) ** 2 / t_scan / 1e12,
+                          cand_per_s=M / (t_knn + t_scan), best_idx=int(res[0][1].item()))))
+
+
+if __name__ == "__main__":
+    _lib.handle()
+    which = sys.argv[1]
+    if which == "cfg2":
+        run_fit_scan("cfg2", *cfg2())
+    elif which == "cfg5":
+        run_fit_scan("cfg5", *cfg5())
+    else:
+        cfg4()
