@@ -41,7 +41,7 @@ UNIT = "candidates/s"
 # Total LML+grad evaluations of one config-3 fit (8 clusters x 17 L-BFGS-B runs), measured by the B200 arm
 # (engine.fit_stats["evals"]); the optimiser is SciPy's own setulb fed by LML/gradients that agree with
 # scikit-learn to ~1e-10, so the reference performs the same number.  Used only to extrapolate the CPU sample.
-EVALS_PER_FIT_CFG3 = 4840
+EVALS_PER_FIT_CFG3 = 4938
 
 PRESETS = {
     "cfg3": dict(n=32768, d=6, C=8, R=16, M=4194304, k=3, name="configs[2]: 6-D piecewise, n=32768, 8 clusters, R=16, M=4194304"),

@@ -277,3 +277,36 @@ def test_roundtrip_properties_midsize():
     ok = ref["std"] > 1e-3
     assert relerr(std.cpu().numpy()[ok], ref["std"][ok]) < 1e-7
     assert int(bi.item()) == ref["best_idx"] and int(bc.item()) == ref["best_cluster"]
+
+
+def test_capi_argument_errors(lib):
+    """LAPACK-style negative return codes for invalid arguments (include/cgp_b200.h conventions)."""
+    import ctypes as C
+
+    L = lib.lib()
+    h = lib.handle()
+    X = dev(np.random.default_rng(0).uniform(size=(10, 2)))
+    th = dev(np.zeros(3))
+    K = torch.empty((10, 10), dtype=torch.float64, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    assert L.cgp_kernel_matrix(None, 0, X.data_ptr(), 10, 2, th.data_ptr(), 0.0, K.data_ptr(), st) == -1
+    assert L.cgp_kernel_matrix(h, 7, X.data_ptr(), 10, 2, th.data_ptr(), 0.0, K.data_ptr(), st) == -2
+    assert L.cgp_kernel_matrix(h, 0, X.data_ptr(), 10, 0, th.data_ptr(), 0.0, K.data_ptr(), st) == -5
+    assert L.cgp_kernel_matrix(h, 0, X.data_ptr(), 10, 17, th.data_ptr(), 0.0, K.data_ptr(), st) == -5
+    assert L.cgp_kernel_matrix(h, 0, X.data_ptr(), 10, 2, None, 0.0, K.data_ptr(), st) == -6
+    lab = dev(np.zeros(10), torch.int64)
+    out = torch.empty(4, dtype=torch.int64, device="cuda")
+    assert L.cgp_knn_labels(h, X.data_ptr(), lab.data_ptr(), 10, 2, 11, 1, X.data_ptr(), 4, out.data_ptr(), st) == -6  # k > n
+    assert L.cgp_knn_labels(h, X.data_ptr(), lab.data_ptr(), 10, 2, 9, 1, X.data_ptr(), 4, out.data_ptr(), st) == -6   # k > CGP_MAX_K
+    assert L.cgp_dgemm_nt(h, X.data_ptr(), X.data_ptr(), K.data_ptr(), 100, 128, 32, st) == -5
+    # a workspace smaller than one pair is refused, not overrun
+    offs = np.array([0, 10], dtype=np.int64)
+    pc = np.zeros(1, dtype=np.int32)
+    ws = torch.empty(1024, dtype=torch.uint8, device="cuda")
+    with pytest.raises(lib.CgpError):
+        lib.lml_grad_batched(X, dev(np.zeros(10)), offs, pc, dev(np.zeros((1, 3))), 1e-5, "matern32", ws)
+    # the binding refuses host / wrong-dtype tensors instead of passing bad pointers
+    with pytest.raises(lib.CgpError):
+        lib.kernel_matrix(X.cpu(), th)
+    with pytest.raises(lib.CgpError):
+        lib.kernel_matrix(X.float(), th)
