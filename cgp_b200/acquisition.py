@@ -33,3 +33,24 @@ def expected_improvement(X, surrogate, X_sample, Y_sample, correct_label, classi
 def expected_improvement_batch(model, candidates):
     """Scores of a whole candidate array through the fused GPU scan: ``model`` is a fitted CGPRegressor."""
     return model.score_candidates(candidates)["score"]
+
+
+def mean_square_prediction_error(X, surrogate, X_sample, Y_sample, correct_label, classify, USE_SKLEARN=True,
+                                 VERBOSE=True, boundary_penalty=lambda a, b: 0):
+    """Second acquisition of the reference (REF/cGP/acquisition.py:34-75), same signature and return convention:
+    joint posterior covariance of [x; X_sample] from ``surrogate.predict(return_cov=True)``, then
+    ``(s_xx - s_xo S_oo s_xo^T + penalty) / len(X_sample)`` — to be minimised, one point per call."""
+    if not USE_SKLEARN:
+        raise NotImplementedError("the GPy branch of the reference is disabled (USE_SKLEARN=True)")
+    my_X = np.asarray(X, dtype=np.float64).reshape(1, -1)
+    if classify.predict(my_X) != np.asarray(correct_label).astype(int):
+        return -0
+    joint = np.vstack((my_X, np.asarray(X_sample, dtype=np.float64)))
+    _, cov = surrogate.predict(joint, return_std=False, return_cov=True)
+    s_xx = cov[0:1, 0:1]
+    s_oo = cov[1:, 1:]
+    s_xo = cov[0:1, 1:]
+    mspe = float((s_xx - s_xo @ s_oo @ s_xo.T).ravel()[0]) + boundary_penalty(my_X, X_sample)
+    if VERBOSE:
+        print("MSPE=", mspe, "\n")
+    return mspe / X_sample.shape[0]

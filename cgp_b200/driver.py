@@ -51,7 +51,7 @@ class cGP_constrained(object):
             raise NotImplementedError("only METHOD_CGP='FREQUENTIST' exists on the scikit-learn path of the reference "
                                       "(REF/cGP/cGP_constrained_module.py:423)")
         if self.ACQUISITION != "EI":
-            raise NotImplementedError("ACQUISITION_CGP='MSPE' is not implemented on the GPU yet (SURVEY.md §8f rank 3)")
+            raise NotImplementedError("ACQUISITION_CGP=MSPE has no dense-scan form yet; use cgp_b200.acquisition.mean_square_prediction_error pointwise")
 
     # ---- hooks (same names / meaning as the reference) ------------------------------------------------------------
     def f_Classify(self):

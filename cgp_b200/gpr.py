@@ -131,18 +131,39 @@ class GaussianProcessRegressor:
     def predict(self, X, return_std=False, return_cov=False):
         if return_std and return_cov:
             raise RuntimeError("At most one of return_std or return_cov can be requested.")  # SK/_gpr.py:405-408
-        if return_cov:
-            raise NotImplementedError("return_cov is not implemented on the GPU path (SURVEY.md §8f rank 3)")
         X = np.asarray(X, dtype=np.float64)
         if X.ndim != 2:
             raise ValueError("Expected 2D array")
         eng = self._eng
+        if return_cov:
+            return self._predict_cov(X)
         ql = torch.full((X.shape[0],), self._c, dtype=torch.int64, device=eng.device)
         mean, std = eng.predict(X, qlabel=ql, return_std=return_std)
         mean = mean.cpu().numpy()
         if return_std:
             return mean, std.cpu().numpy()
         return mean
+
+    def _predict_cov(self, X):
+        """Joint posterior covariance, SK/_gpr.py:464-478: ``kernel_(X) - V^T V`` with ``V = L^-1 K*^T``, through the
+        same DMMA tile GEMM as the factorisation (W = L^-1 is resident): Vt = K* W^T, V^T V = Vt Vt^T."""
+        eng, c = self._eng, self._c
+        m = X.shape[0]
+        n, npad = int(eng.counts[c]), int(eng.npad[c])
+        mpad = _lib.padded_n(max(m, 1))
+        dev = eng.device
+        Xd = torch.from_numpy(np.ascontiguousarray(X)).to(dev)
+        th = eng.model["theta_dev"][c].contiguous()
+        Xt = eng.Xs[int(eng.offs[c]):int(eng.offs[c + 1])]
+        Ks = torch.zeros((mpad, npad), dtype=torch.float64, device=dev)
+        Ks[:m, :n] = _lib.kernel_cross(Xd, Xt, th, eng.kind)
+        W = eng.model["W"][int(eng.moff[c]):int(eng.moff[c + 1])].view(npad, npad)
+        Vt = _lib.dgemm_nt(Ks, W)  # [mpad, npad], Vt[q, i] = sum_k K*[q, k] W[i, k]
+        VtV = _lib.dgemm_nt(Vt, Vt)[:m, :m]
+        ql = torch.full((m,), c, dtype=torch.int64, device=dev)
+        mean, _ = eng.predict(Xd, qlabel=ql, return_std=False)
+        cov =(_lib.kernel_matrix(Xd, th, eng.kind, 0.0) - VtV) * (eng.y_std[c] ** 2)
+        return mean.cpu().numpy(), cov.cpu().numpy()
 
     def log_marginal_likelihood(self, theta=None, eval_gradient=False, clone_kernel=True):
         if theta is None:

@@ -182,6 +182,31 @@ def case_fit_select(name, n, d, C, R, M, seed, kind="matern32", n_pointwise=64):
     print(name, "best", best, "thetas", [out[f"c{c}_theta"] for c in range(C)])
 
 
+def case_cov_mspe(name, n, d, seed, m=40, n_mspe=6):
+    """predict(return_cov=True) and the reference's mean_square_prediction_error (REF/cGP/acquisition.py:34-75)
+    through sklearn objects, at a fixed theta (optimizer=None)."""
+    from sklearn.neighbors import KNeighborsClassifier
+
+    acq = _ref_acquisition()
+    rng = np.random.default_rng(seed)
+    X = rng.uniform(size=(n, d))
+    y = _piecewise(X, rng)
+    theta = np.array([-0.8] * d + [-3.0])
+    g = _ref_gpr(d, 0)
+    g.kernel = g.kernel.clone_with_theta(theta)
+    g.optimizer = None
+    g.fit(X, y.reshape(-1, 1))
+    Q = rng.uniform(size=(m, d))
+    mean, cov = g.predict(Q, return_cov=True)
+    clf = KNeighborsClassifier(n_neighbors=3).fit(X, np.zeros(n, dtype=np.int64))
+    mspe = np.array([acq.mean_square_prediction_error(X=Q[i], surrogate=g, X_sample=X, Y_sample=y.reshape(-1, 1),
+                                                      correct_label=np.float64(0), classify=clf, VERBOSE=False)
+                     for i in range(n_mspe)])
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), X=X, y=y, theta=theta, Q=Q, mean=np.asarray(mean).reshape(-1),
+                        cov=cov, mspe=mspe)
+    print(name, "cov diag", np.diag(cov)[:4], "mspe", mspe)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     bukin()
@@ -190,3 +215,4 @@ if __name__ == "__main__":
     case_lml("lml_rbf_n150_d3", 150, 3, "rbf", 13)
     case_fit_select("fit_select_d2", n=120, d=2, C=2, R=20, M=2000, seed=21)
     case_fit_select("fit_select_d6", n=360, d=6, C=3, R=4, M=3000, seed=22)
+    case_cov_mspe("cov_mspe_d3", n=150, d=3, seed=31)

@@ -310,3 +310,27 @@ def test_capi_argument_errors(lib):
         lib.kernel_matrix(X.cpu(), th)
     with pytest.raises(lib.CgpError):
         lib.kernel_matrix(X.float(), th)
+
+
+def test_return_cov_and_mspe_vs_reference():
+    """predict(return_cov=True) (SK/_gpr.py:464-478) and the reference's mean_square_prediction_error
+    (REF/cGP/acquisition.py:34-75) against outputs of the reference's own code (tests/golden/cov_mspe_d3.npz)."""
+    from cgp_b200 import GaussianProcessRegressor, KNeighborsClassifier
+    from cgp_b200.acquisition import mean_square_prediction_error
+    from sklearn.gaussian_process.kernels import Matern, WhiteKernel
+
+    g = load_golden("cov_mspe_d3")
+    X, y, Q = g["X"], g["y"], g["Q"]
+    k = (Matern(length_scale=np.ones(3), length_scale_bounds=(1e-05, 100000.0), nu=3 / 2) +
+         WhiteKernel(noise_level=1.0, noise_level_bounds=(1e-05, 100000.0))).clone_with_theta(g["theta"])
+    m = GaussianProcessRegressor(kernel=k, alpha=1e-5, normalize_y=True, optimizer=None, random_state=0).fit(X, y.reshape(-1, 1))
+    mean, cov = m.predict(Q, return_cov=True)
+    assert relerr(mean, g["mean"]) < RTOL
+    assert np.max(np.abs(cov - g["cov"])) < 1e-9 * np.max(np.abs(g["cov"]))
+    with pytest.raises(RuntimeError):
+        m.predict(Q, return_std=True, return_cov=True)
+    clf = KNeighborsClassifier(3).fit(X, np.zeros(X.shape[0], dtype=np.int64))
+    for i, want in enumerate(g["mspe"]):
+        got = mean_square_prediction_error(X=Q[i], surrogate=m, X_sample=X, Y_sample=y.reshape(-1, 1),
+                                           correct_label=np.float64(0), classify=clf, VERBOSE=False)
+        assert abs(got - want) <= 1e-7 * abs(want)
