@@ -106,25 +106,40 @@ class ClusterGPEngine:
         return self._ws
 
     # ------------------------------------------------------------------ LML
-    def lml_grad(self, pair_cluster, thetas, want_grad=True):
-        """Batched log-marginal likelihood (+ gradient) for pairs (cluster, theta).  Host arrays in/out.
-        Non-PD -> (-inf, 0) as SK/_gpr.py:592-593."""
+    def lml_grad_submit(self, pair_cluster, thetas, want_grad=True):
+        """Enqueue a batched LML (+ gradient) evaluation and the device->pinned-host copies of its results.
+        Returns a ticket for lml_grad_collect; nothing here waits for the device."""
         pair_cluster = np.asarray(pair_cluster, dtype=np.int32)
         thetas = np.ascontiguousarray(np.asarray(thetas, dtype=np.float64).reshape(len(pair_cluster), self.P))
         need = _lib.lml_workspace_bytes(self.offs, pair_cluster, self.d)
         ws = self._workspace(need)
-        th = torch.from_numpy(thetas).to(self.device)
+        th = torch.from_numpy(thetas).to(self.device, non_blocking=True)
         lml, grad, info = _lib.lml_grad_batched(self.Xs, self.yn, self.offs, pair_cluster, th, self.alpha, self.kind,
                                                 ws, want_grad)
-        lml = lml.cpu().numpy()
-        info = info.cpu().numpy()
+        host = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True) if t is not None else None for t in (lml, grad, info)]
+        for h, t in zip(host, (lml, grad, info)):
+            if t is not None:
+                h.copy_(t, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        return host, ev, (th, lml, grad, info)  # device tensors are kept alive until collected
+
+    def lml_grad_collect(self, ticket):
+        """-> (lml, grad | None, info) host arrays; non-PD -> (-inf, 0) as SK/_gpr.py:592-593."""
+        host, ev, _keep = ticket
+        ev.synchronize()
+        lml, info = host[0].numpy().copy(), host[2].numpy().copy()
         bad = info != 0
         lml[bad] = -np.inf
-        if want_grad:
-            grad = grad.cpu().numpy()
+        grad = None
+        if host[1] is not None:
+            grad = host[1].numpy().copy()
             grad[bad] = 0.0
-            return lml, grad, info
-        return lml, None, info
+        return lml, grad, info
+
+    def lml_grad(self, pair_cluster, thetas, want_grad=True):
+        """Batched log-marginal likelihood (+ gradient) for pairs (cluster, theta).  Host arrays in/out."""
+        return self.lml_grad_collect(self.lml_grad_submit(pair_cluster, thetas, want_grad))
 
     # ------------------------------------------------------------------ fit
     def fit(self, n_restarts, seed=0, theta0=None, bounds=None, optimize=True):
@@ -157,7 +172,17 @@ class ClusterGPEngine:
             t_eval[0] += time.perf_counter() - t0
             return -lml, -grad
 
-        xs, fs, nfev, nit, steps = minimize_lockstep(eval_batch, x0s, lo, hi)
+        def submit(idx, Xs):
+            n_eval[0] += len(idx)
+            return self.lml_grad_submit(pc_all[idx], Xs, True)
+
+        def collect(ticket):
+            t0 = time.perf_counter()
+            lml, grad, _ = self.lml_grad_collect(ticket)
+            t_eval[0] += time.perf_counter() - t0
+            return -lml, -grad
+
+        xs, fs, nfev, nit, steps = minimize_lockstep(eval_batch, x0s, lo, hi, submit=submit, collect=collect)
         t_opt = time.perf_counter() - t_fit0
         rows = torch.from_numpy(np.concatenate([xs, fs[:, None]], axis=1).reshape(len(mine), P + 1)).to(self.device)
         table = cdist.gather_pair_rows(rows, n_pairs, rank, ws).cpu().numpy().reshape(C, R1, P + 1)

@@ -5,7 +5,9 @@ The optimiser arithmetic stays on the host and is SciPy's own reverse-communicat
 _lbfgsb_py.py:272-461: m=10, factr=ftol/eps with ftol=2.22e-9, pgtol=1e-5, maxls=20, maxiter=maxfun=15000),
 which is what ``GaussianProcessRegressor._constrained_optimization`` calls (SK/gaussian_process/_gpr.py:658-674).
 Instead of one objective call per run, every run that is waiting for (f, g) is evaluated in ONE batched GPU
-launch per lock-step.
+launch per lock-step.  With many runs the set is split in two groups that alternate: while the GPU evaluates one
+group the host advances the state machines of the other, so the host time disappears from the critical path.
+Every run still sees exactly its own sequence of (x -> f, g) evaluations, so results do not depend on the grouping.
 """
 from __future__ import annotations
 
@@ -74,24 +76,55 @@ class _Run:
         self.nfev += 1
 
 
-def minimize_lockstep(eval_batch, x0s, lo, hi, max_steps=100000):
+def minimize_lockstep(eval_batch, x0s, lo, hi, max_steps=100000, submit=None, collect=None, pipeline_min=256):
     """Minimise len(x0s) independent problems.
 
     eval_batch(idx: int array [b], X: float array [b, n]) -> (f [b], g [b, n]) evaluates problems `idx` at `X`.
-    Returns (x [R, n], f [R], nfev [R], nit [R], n_lockstep)."""
+    Optional asynchronous form: ``submit(idx, X) -> ticket`` enqueues the evaluation, ``collect(ticket) -> (f, g)``
+    waits for it; with both given and at least `pipeline_min` runs waiting, two groups alternate so that host and
+    device work overlap.  Returns (x [R, n], f [R], nfev [R], nit [R], n_lockstep)."""
     runs = [_Run(np.asarray(x0), lo, hi) for x0 in x0s]
     waiting = [i for i, r in enumerate(runs) if r.advance()]
     steps = 0
-    while waiting and steps < max_steps:
-        idx = np.asarray(waiting, dtype=np.int64)
-        X = np.stack([runs[i].x.copy() for i in waiting])
-        f, g = eval_batch(idx, X)
+
+    def take(group):
+        idx = np.asarray(group, dtype=np.int64)
+        return idx, np.stack([runs[i].x.copy() for i in group])
+
+    def absorb(group, f, g):
         nxt = []
-        for k, i in enumerate(waiting):
+        for k, i in enumerate(group):
             runs[i].feed(f[k], g[k])
             if runs[i].advance():
                 nxt.append(i)
-        waiting = nxt
+        return nxt
+
+    if submit is not None and collect is not None and len(waiting) >= pipeline_min:
+        # two alternating groups; falls back to one group once few runs remain
+        half = len(waiting) // 2
+        ga, gb = waiting[:half], waiting[half:]
+        ta = submit(*take(ga))
+        while steps < max_steps:
+            tb = submit(*take(gb)) if gb else None
+            ga = absorb(ga, *collect(ta))  # host works on A while the device runs B
+            steps += 1
+            if len(ga) + len(gb) < pipeline_min:
+                if tb is not None:
+                    gb = absorb(gb, *collect(tb))
+                waiting = ga + gb
+                break
+            ta = submit(*take(ga)) if ga else None
+            if tb is not None:
+                gb = absorb(gb, *collect(tb))  # host works on B while the device runs A
+            if ta is None:
+                waiting = gb
+                break
+        else:
+            waiting = []
+    while waiting and steps < max_steps:
+        idx, X = take(waiting)
+        f, g = eval_batch(idx, X)
+        waiting = absorb(waiting, f, g)
         steps += 1
     xs = np.stack([r.x for r in runs])
     fs = np.array([float(r.f) for r in runs])

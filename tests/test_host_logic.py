@@ -86,3 +86,33 @@ def test_plugin_contracts():
     XY = np.random.default_rng(0).normal(size=(40, 3))
     lab = importlib.import_module("cgp_b200.plugins.KMeans2").f_Cluster(0).fit_predict(XY)
     assert lab.shape == (40,)
+
+
+def test_pipelined_lockstep_equals_plain():
+    """Two alternating groups (host/device overlap) give every run the same evaluation sequence as one group."""
+    rng = np.random.default_rng(1)
+    n_runs, dim = 40, 3
+    A = rng.uniform(0.5, 2.0, size=(n_runs, dim))
+    c = rng.uniform(-1, 1, size=(n_runs, dim))
+
+    def fg(idx, Xs):
+        a, cc = A[idx], c[idx]
+        r = Xs - cc
+        f = (a * r ** 2).sum(1) + 0.1 * np.sin(3 * Xs).sum(1)
+        g = 2 * a * r + 0.3 * np.cos(3 * Xs)
+        return f, g
+
+    x0 = [rng.uniform(-2, 2, size=dim) for _ in range(n_runs)]
+    lo, hi = np.full(dim, -3.0), np.full(dim, 3.0)
+    plain = minimize_lockstep(fg, x0, lo, hi)
+    tickets, counter = {}, [0]
+
+    def submit(idx, Xs):
+        counter[0] += 1
+        tickets[counter[0]] = fg(idx, Xs)
+        return counter[0]
+
+    piped = minimize_lockstep(fg, x0, lo, hi, submit=submit, collect=lambda t: tickets.pop(t), pipeline_min=8)
+    assert np.array_equal(plain[0], piped[0]) and np.array_equal(plain[1], piped[1])
+    assert np.array_equal(plain[2], piped[2]) and np.array_equal(plain[3], piped[3])
+    assert not tickets

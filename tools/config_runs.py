@@ -75,7 +75,8 @@ def run_fit_scan(name, X, y, lab, Q, R, extra):
         t_fit, _ = sync_time(lambda: eng.fit(R, seed=0))
         t_knn, ql = sync_time(lambda: eng.route(Qd, 3))
         t_scan, res = sync_time(lambda: eng.ei_scan(Qd, 3, qlabel=ql))
-    out.update(fit_s=t_fit, evals=eng.fit_stats["evals"], lockstep=eng.fit_stats["lockstep"], knn_s=t_knn, scan_s=t_scan,
+    out.update(fit_s=t_fit, evals=eng.fit_stats["evals"], lockstep=eng.fit_stats["lockstep"],
+               fit_eval_wall_s=eng.fit_stats["eval_s"], fit_optimizer_host_s=eng.fit_stats["optimizer_host_s"], knn_s=t_knn, scan_s=t_scan,
                iteration_s=t_fit + t_knn + t_scan, cand_per_s_acq=Q.shape[0] / (t_knn + t_scan),
                best=dict(score=float(res[0][0].item()), idx=int(res[0][1].item()), cluster=int(res[0][2].item())))
     print(json.dumps(out))
