@@ -7,6 +7,7 @@ over ranks.  No CPU fallback.
 from __future__ import annotations
 
 import math
+import os
 import time
 
 import numpy as np
@@ -182,7 +183,8 @@ class ClusterGPEngine:
             t_eval[0] += time.perf_counter() - t0
             return -lml, -grad
 
-        xs, fs, nfev, nit, steps = minimize_lockstep(eval_batch, x0s, lo, hi, submit=submit, collect=collect)
+        xs, fs, nfev, nit, steps = minimize_lockstep(eval_batch, x0s, lo, hi, submit=submit, collect=collect,
+                                                     pipeline_min=int(os.environ.get("CGP_PIPELINE_MIN", "256")))
         t_opt = time.perf_counter() - t_fit0
         rows = torch.from_numpy(np.concatenate([xs, fs[:, None]], axis=1).reshape(len(mine), P + 1)).to(self.device)
         table = cdist.gather_pair_rows(rows, n_pairs, rank, ws).cpu().numpy().reshape(C, R1, P + 1)
