@@ -143,9 +143,15 @@ class ClusterGPEngine:
         return self.lml_grad_collect(self.lml_grad_submit(pair_cluster, thetas, want_grad))
 
     # ------------------------------------------------------------------ fit
-    def fit(self, n_restarts, seed=0, theta0=None, bounds=None, optimize=True):
-        """All clusters x (R+1) restarts in lock-step (SK/_gpr.py:296-340), sharded round-robin over ranks,
-        then the final factorisation at each cluster's best theta (SK/_gpr.py:349-367)."""
+    def fit(self, n_restarts, seed=0, theta0=None, bounds=None, optimize=True, shard_mode=None):
+        """All clusters x (R+1) restarts in lock-step (SK/_gpr.py:296-340), sharded over ranks, then the final
+        factorisation at each cluster's best theta (SK/_gpr.py:349-367).
+
+        shard_mode "static": the (cluster, restart) pairs are dealt round-robin once; each rank optimises its own pairs
+        and one all-gather of (theta*, -lml) rows follows.  "balanced": every rank keeps all state machines and in each
+        lock-step evaluates only its share of the waiting runs (see lbfgs.minimize_lockstep)."""
+        if shard_mode is None:
+            shard_mode = os.environ.get("CGP_SHARD_MODE", "balanced")
         rank, ws = cdist.world()
         P, C = self.P, self.C
         lo = np.full(P, LOG_LO) if bounds is None else np.asarray(bounds, float)[:, 0]
@@ -159,22 +165,26 @@ class ClusterGPEngine:
             self._factorize()
             return self
         n_pairs = C * R1  # pair p = (cluster p // R1, run p % R1)
-        mine = cdist.my_pairs(n_pairs, rank, ws)
+        balanced = ws > 1 and shard_mode == "balanced"
+        mine = list(range(n_pairs)) if balanced else cdist.my_pairs(n_pairs, rank, ws)
         pc_all = np.asarray([p // R1 for p in mine], dtype=np.int32)
         x0s = [starts[p % R1] for p in mine]
         n_eval = [0]
         t_eval = [0.0]
+        evals_c = np.zeros(C, dtype=np.int64)  # evaluations THIS rank performed, per cluster
         t_fit0 = time.perf_counter()
 
         def eval_batch(idx, Xs):
             t0 = time.perf_counter()
             lml, grad, _ = self.lml_grad(pc_all[idx], Xs, True)
             n_eval[0] += len(idx)
+            np.add.at(evals_c, pc_all[idx], 1)
             t_eval[0] += time.perf_counter() - t0
             return -lml, -grad
 
         def submit(idx, Xs):
             n_eval[0] += len(idx)
+            np.add.at(evals_c, pc_all[idx], 1)
             return self.lml_grad_submit(pc_all[idx], Xs, True)
 
         def collect(ticket):
@@ -183,18 +193,31 @@ class ClusterGPEngine:
             t_eval[0] += time.perf_counter() - t0
             return -lml, -grad
 
+        shard = None
+        if balanced:
+            def allreduce(buf):
+                t = torch.from_numpy(buf).to(self.device)
+                torch.distributed.all_reduce(t)
+                return t.cpu().numpy()
+
+            shard = dict(rank=rank, world=ws, cost=self.counts[pc_all].astype(np.float64) ** 3, allreduce=allreduce)
         xs, fs, nfev, nit, steps = minimize_lockstep(eval_batch, x0s, lo, hi, submit=submit, collect=collect,
-                                                     pipeline_min=int(os.environ.get("CGP_PIPELINE_MIN", "256")))
+                                                     pipeline_min=int(os.environ.get("CGP_PIPELINE_MIN", "256")),
+                                                     shard=shard)
         t_opt = time.perf_counter() - t_fit0
-        rows = torch.from_numpy(np.concatenate([xs, fs[:, None]], axis=1).reshape(len(mine), P + 1)).to(self.device)
-        table = cdist.gather_pair_rows(rows, n_pairs, rank, ws).cpu().numpy().reshape(C, R1, P + 1)
+        rows = np.concatenate([xs, fs[:, None]], axis=1).reshape(len(mine), P + 1)
+        if balanced:  # every rank already holds every run's result
+            table = rows.reshape(C, R1, P + 1)
+        else:
+            table = cdist.gather_pair_rows(torch.from_numpy(rows).to(self.device), n_pairs, rank, ws)
+            table = table.cpu().numpy().reshape(C, R1, P + 1)
         self.run_thetas = table[:, :, :P]
         self.run_values = table[:, :, P]
         best = np.argmin(self.run_values, axis=1)  # first minimum in run order, SK/_gpr.py:336-337
         self.theta = np.stack([self.run_thetas[c, best[c]] for c in range(C)])
         self.fit_stats = dict(lockstep=steps, evals=int(n_eval[0]), nfev=nfev, nit=nit, pairs_local=len(mine),
                               pairs_total=n_pairs, eval_s=t_eval[0], optimizer_host_s=t_opt - t_eval[0],
-                              evals_per_cluster=np.bincount(pc_all, weights=nfev, minlength=C).astype(np.int64))
+                              evals_per_cluster=evals_c, shard_mode=("balanced" if balanced else "static"))
         self._factorize()
         return self
 

@@ -76,13 +76,19 @@ class _Run:
         self.nfev += 1
 
 
-def minimize_lockstep(eval_batch, x0s, lo, hi, max_steps=100000, submit=None, collect=None, pipeline_min=256):
+def minimize_lockstep(eval_batch, x0s, lo, hi, max_steps=100000, submit=None, collect=None, pipeline_min=256,
+                      shard=None):
     """Minimise len(x0s) independent problems.
 
     eval_batch(idx: int array [b], X: float array [b, n]) -> (f [b], g [b, n]) evaluates problems `idx` at `X`.
     Optional asynchronous form: ``submit(idx, X) -> ticket`` enqueues the evaluation, ``collect(ticket) -> (f, g)``
     waits for it; with both given and at least `pipeline_min` runs waiting, two groups alternate so that host and
-    device work overlap.  Returns (x [R, n], f [R], nfev [R], nit [R], n_lockstep)."""
+    device work overlap.
+    Multi-rank form: ``shard = dict(rank, world, cost [R], allreduce)``.  Every rank holds ALL state machines; in each
+    lock-step the waiting runs are dealt to the ranks (heaviest first, round-robin), each rank evaluates only its share
+    and ``allreduce`` (sum over ranks of a [b, n+1] array whose foreign rows are zero) hands every rank all (f, g).
+    The machines then advance identically everywhere, so the work stays balanced as runs finish at different times.
+    Returns (x [R, n], f [R], nfev [R], nit [R], n_lockstep)."""
     runs = [_Run(np.asarray(x0), lo, hi) for x0 in x0s]
     waiting = [i for i, r in enumerate(runs) if r.advance()]
     steps = 0
@@ -99,7 +105,8 @@ def minimize_lockstep(eval_batch, x0s, lo, hi, max_steps=100000, submit=None, co
                 nxt.append(i)
         return nxt
 
-    if submit is not None and collect is not None and len(waiting) >= pipeline_min:
+    if submit is not None and collect is not None and len(waiting) >= pipeline_min and not (
+            shard is not None and shard["world"] > 1):
         # two alternating groups; falls back to one group once few runs remain
         half = len(waiting) // 2
         ga, gb = waiting[:half], waiting[half:]
@@ -121,9 +128,21 @@ def minimize_lockstep(eval_batch, x0s, lo, hi, max_steps=100000, submit=None, co
                 break
         else:
             waiting = []
+    sharded = shard is not None and shard["world"] > 1
     while waiting and steps < max_steps:
         idx, X = take(waiting)
-        f, g = eval_batch(idx, X)
+        if sharded:
+            order = np.argsort(-np.asarray(shard["cost"])[idx], kind="stable")
+            mine = np.sort(order[shard["rank"]::shard["world"]])
+            buf = np.zeros((len(idx), X.shape[1] + 1))
+            if len(mine):
+                fm, gm = eval_batch(idx[mine], X[mine])
+                buf[mine, 0] = fm
+                buf[mine, 1:] = gm
+            buf = shard["allreduce"](buf)
+            f, g = buf[:, 0], buf[:, 1:]
+        else:
+            f, g = eval_batch(idx, X)
         waiting = absorb(waiting, f, g)
         steps += 1
     xs = np.stack([r.x for r in runs])

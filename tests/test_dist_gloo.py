@@ -43,7 +43,34 @@ def _worker(rank, world, port, q):
         s, i, c, x, owner = cdist.reduce_best(torch.tensor([score[j]]), torch.tensor([j]), torch.tensor([cluster[j]]),
                                               torch.from_numpy(Q[j].copy()), rank, world)
         ok_sel = (i == 900 and c == 1 and s == 2.0 and np.array_equal(x.numpy(), Q[900]) and owner == 1)
-        q.put((rank, ok_fit, ok_sel, (lo, hi)))
+        # ---- balanced sharded lock-step: replicated L-BFGS-B state machines, each rank evaluates its share
+        from cgp_b200.lbfgs import minimize_lockstep
+
+        n_runs, dim = 13, 3
+        A = rng.uniform(0.5, 2.0, size=(n_runs, dim))
+        cen = rng.uniform(-1, 1, size=(n_runs, dim))
+        calls = [0]
+
+        def fg(idx, Xs):
+            calls[0] += len(idx)
+            r = Xs - cen[idx]
+            return (A[idx] * r ** 2).sum(1) + 0.1 * np.sin(3 * Xs).sum(1), 2 * A[idx] * r + 0.3 * np.cos(3 * Xs)
+
+        x0 = [np.full(dim, 0.3 * (i % 5) - 0.5) for i in range(n_runs)]
+        lo3, hi3 = np.full(dim, -3.0), np.full(dim, 3.0)
+        plain = minimize_lockstep(fg, x0, lo3, hi3)
+        total_plain = calls[0]
+        calls[0] = 0
+
+        def allreduce(buf):
+            t = torch.from_numpy(buf.copy())
+            dist.all_reduce(t)
+            return t.numpy()
+
+        sh = minimize_lockstep(fg, x0, lo3, hi3, shard=dict(rank=rank, world=world, cost=np.arange(n_runs) % 3 + 1.0,
+                                                            allreduce=allreduce))
+        ok_bal = all(np.array_equal(a, b) for a, b in zip(plain[:4], sh[:4])) and calls[0] < 0.7 * total_plain
+        q.put((rank, ok_fit, ok_sel and ok_bal, (lo, hi)))
     finally:
         dist.destroy_process_group()
 
