@@ -151,7 +151,7 @@ class ClusterGPEngine:
         and one all-gather of (theta*, -lml) rows follows.  "balanced": every rank keeps all state machines and in each
         lock-step evaluates only its share of the waiting runs (see lbfgs.minimize_lockstep)."""
         if shard_mode is None:
-            shard_mode = os.environ.get("CGP_SHARD_MODE", "balanced")
+            shard_mode = os.environ.get("CGP_SHARD_MODE", "static")  # measured on 8 B200: balanced 3.19 s/step, static 3.24
         rank, ws = cdist.world()
         P, C = self.P, self.C
         lo = np.full(P, LOG_LO) if bounds is None else np.asarray(bounds, float)[:, 0]
