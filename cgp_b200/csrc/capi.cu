@@ -2,6 +2,7 @@
 // fixed sequence of asynchronous kernel launches on the caller's stream.
 #include <cstdio>
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -48,6 +49,7 @@ struct HandleImpl : cgp_handle {
     long long launches[CLS_COUNT];
     // second stream: the triangular-inverse chain of panel s runs beside the Cholesky chain of panel s+1
     cudaStream_t s2;
+    int tile_mode;  // 0 = by launch size, 1 = always 128x128 CTAs, 2 = always the small shapes
     std::vector<cudaEvent_t> panel_ev;
     cudaEvent_t join_ev;
 };
@@ -118,14 +120,26 @@ extern "C" int cgp_create(cgp_handle** out, int device) {
     }
     for (int i = 0; i < CLS_COUNT; ++i) h->ms[i] = 0.0, h->launches[i] = 0;
     CGP_CHECK(set_smem(k_dgemm_nt, GEMM_SMEM_BYTES));
-    CGP_CHECK(set_smem(k_potrf_update, GEMM_SMEM_BYTES));
-    CGP_CHECK(set_smem(k_potrf_panel, GEMM_SMEM_BYTES));
-    CGP_CHECK(set_smem(k_potrf_trail, GEMM_SMEM_BYTES));
-    CGP_CHECK(set_smem(k_trtri_trail, GEMM_SMEM_BYTES));
-    CGP_CHECK(set_smem(k_trtri_acc, GEMM_SMEM_BYTES));
-    CGP_CHECK(set_smem(k_trtri_scale, GEMM_SMEM_BYTES));
-    CGP_CHECK(set_smem(k_lauum, GEMM_SMEM_BYTES));
+#define SET3(K)                                                                       \
+    CGP_CHECK(set_smem(K<128, 128>, GEMM_SMEM_BYTES_T(128, 128)));                    \
+    CGP_CHECK(set_smem(K<64, 64>, GEMM_SMEM_BYTES_T(64, 64)))
+#define SET2(K)                                                                       \
+    CGP_CHECK(set_smem(K<128, 128>, GEMM_SMEM_BYTES_T(128, 128)));                    \
+    CGP_CHECK(set_smem(K<64, 128>, GEMM_SMEM_BYTES_T(64, 128)))
+    SET3(k_potrf_update);
+    SET3(k_potrf_trail);
+    SET3(k_trtri_acc);
+    SET3(k_trtri_trail);
+    SET3(k_lauum);
+    SET2(k_potrf_panel);
+    SET2(k_trtri_scale);
+#undef SET3
+#undef SET2
     CGP_CHECK(set_smem(k_predict_vnorm, GEMM_SMEM_BYTES));
+    {
+        const char* e = getenv("CGP_TILE_MODE");  // "big" | "small" | unset = by launch size (results are bit-identical)
+        h->tile_mode = (e && !strcmp(e, "big")) ? 1 : (e && !strcmp(e, "small")) ? 2 : 0;
+    }
     CGP_CHECK(set_smem(k_potrf_diag, DIAG_SMEM_BYTES));
     *out = h;
     return 0;
@@ -250,6 +264,29 @@ extern "C" int cgp_dgemm_nt(cgp_handle* hh, const double* A, const double* B, do
 // ------------------------------------------------------------------------------------------------
 // batched factorisation pipeline
 // ------------------------------------------------------------------------------------------------
+// A launch with fewer 128x128 tiles than ~4 waves of SMs is split into 64x64 (or, for in-place steps, 64x128) pieces:
+// same bits, 2-4x more CTAs, shorter dependent steps (see gemm_nt.cuh).
+static inline bool small_tiles(const HandleImpl* h, long long tiles) {
+    if (h->tile_mode == 1) return false;
+    if (h->tile_mode == 2) return true;
+    return tiles < 4LL * h->sm_count;
+}
+// GL(class, stream, kernel, tiles_x, n_mats, args...): out-of-place tile kernels;  GLI: in-place (tile <- tile * D^T)
+#define GL(cls, st, K, tx, nm, ...)                                                                                   \
+    do {                                                                                                              \
+        if (small_tiles(h, (long long)(tx) * (nm)))                                                                    \
+            KL(h, cls, st, (K<64, 64><<<dim3((tx)*4, nm), CGP_GEMM_THREADS, GEMM_SMEM_BYTES_T(64, 64), st>>>(__VA_ARGS__))); \
+        else                                                                                                          \
+            KL(h, cls, st, (K<128, 128><<<dim3(tx, nm), CGP_GEMM_THREADS, GEMM_SMEM_BYTES_T(128, 128), st>>>(__VA_ARGS__))); \
+    } while (0)
+#define GLI(cls, st, K, tx, nm, ...)                                                                                  \
+    do {                                                                                                              \
+        if (small_tiles(h, (long long)(tx) * (nm)))                                                                    \
+            KL(h, cls, st, (K<64, 128><<<dim3((tx)*2, nm), CGP_GEMM_THREADS, GEMM_SMEM_BYTES_T(64, 128), st>>>(__VA_ARGS__))); \
+        else                                                                                                          \
+            KL(h, cls, st, (K<128, 128><<<dim3(tx, nm), CGP_GEMM_THREADS, GEMM_SMEM_BYTES_T(128, 128), st>>>(__VA_ARGS__))); \
+    } while (0)
+
 struct Batch {
     int nm = 0, Tmax = 0, npad_max = 0, ntl_max = 0;
     MatMeta* meta = nullptr;  // device
@@ -280,10 +317,10 @@ static int run_pipeline(HandleImpl* h, int kind, const double* X, const double* 
         const int c1 = std::min(T, c0 + CGP_PANEL);
         for (int j = c0; j < c1; ++j) {
             if (j > c0)
-                KL(h, CLS_POTRF_UPDATE, s, k_potrf_update<<<dim3(T - j, nm), CGP_GEMM_THREADS, GEMM_SMEM_BYTES, s>>>(b.A, b.meta, j, c0));
+                GL(CLS_POTRF_UPDATE, s, k_potrf_update, T - j, nm, b.A, b.meta, j, c0);
             KL(h, CLS_POTRF_DIAG, s, k_potrf_diag<<<nm, 256, DIAG_SMEM_BYTES, s>>>(b.A, b.U, b.D, b.logdet, info, b.meta, j, T));
             if (j + 1 < T)
-                KL(h, CLS_POTRF_PANEL, s, k_potrf_panel<<<dim3(T - j - 1, nm), CGP_GEMM_THREADS, GEMM_SMEM_BYTES, s>>>(b.A, b.D, b.meta, j));
+                GLI(CLS_POTRF_PANEL, s, k_potrf_panel, T - j - 1, nm, b.A, b.D, b.meta, j);
         }
         if (fork) {
             CGP_CHECK(cudaEventRecord(h->panel_ev[p], s));
@@ -291,15 +328,15 @@ static int run_pipeline(HandleImpl* h, int kind, const double* X, const double* 
         }
         if (c1 < T) {
             const int Tt = T - c1;
-            KL(h, CLS_POTRF_TRAIL, s, k_potrf_trail<<<dim3(Tt * (Tt + 1) / 2, nm), CGP_GEMM_THREADS, GEMM_SMEM_BYTES, s>>>(b.A, b.meta, c0, c1));
+            GL(CLS_POTRF_TRAIL, s, k_potrf_trail, Tt * (Tt + 1) / 2, nm, b.A, b.meta, c0, c1);
         }
         for (int i = std::max(c0, 1); i < c1; ++i) {
             if (i > c0)
-                KL(h, CLS_TRTRI_ACC, st, k_trtri_acc<<<dim3(i, nm), CGP_GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(b.A, b.U, b.meta, i, c0));
-            KL(h, CLS_TRTRI_SCALE, st, k_trtri_scale<<<dim3(i, nm), CGP_GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(b.U, b.D, b.meta, i));
+                GL(CLS_TRTRI_ACC, st, k_trtri_acc, i, nm, b.A, b.U, b.meta, i, c0);
+            GLI(CLS_TRTRI_SCALE, st, k_trtri_scale, i, nm, b.U, b.D, b.meta, i);
         }
         if (c1 < T)
-            KL(h, CLS_TRTRI_TRAIL, st, k_trtri_trail<<<dim3(c1 * (T - c1), nm), CGP_GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(b.A, b.U, b.meta, c0, c1, T));
+            GL(CLS_TRTRI_TRAIL, st, k_trtri_trail, c1 * (T - c1), nm, b.A, b.U, b.meta, c0, c1, T);
     }
     if (fork) {
         CGP_CHECK(cudaEventRecord(h->join_ev, st));
@@ -309,7 +346,7 @@ static int run_pipeline(HandleImpl* h, int kind, const double* X, const double* 
     KL(h, CLS_SOLVE, s, k_solve_a<<<dim3(b.npad_max / 8, nm), 256, 0, s>>>(b.U, b.z, b.a, b.meta, b.npad_max));
     KL(h, CLS_SOLVE, s, k_lml_finish<<<nm, 256, 0, s>>>(b.z, b.logdet, info, lml, b.meta, b.npad_max, T));
     if (grad) {
-        KL(h, CLS_LAUUM, s, k_lauum<<<gl, CGP_GEMM_THREADS, GEMM_SMEM_BYTES, s>>>(b.A, b.U, b.meta));
+        GL(CLS_LAUUM, s, k_lauum, b.ntl_max, nm, b.A, b.U, b.meta);
         const int dm = dmax_for(d);
         const size_t gs = xs + (2 * CGP_TILE + 8 * dm) * 8;
 #define LAUNCH_GRAD(KIND, DM)                                                                                        \

@@ -176,3 +176,31 @@ def test_config4_shape_single_large_cluster():
     assert relerr(mean.cpu().numpy(), mu) < 1e-7
     ok = sd > 1e-3
     assert relerr(std.cpu().numpy()[ok], sd[ok]) < 1e-6
+
+
+def test_tile_shapes_are_bit_identical():
+    """The latency shapes (64x64 / 64x128 CTA pieces) and the throughput shape (128x128) of the DMMA tile kernels must
+    produce the same bits: the choice depends on the launch size, and results must not depend on batch or rank count."""
+    import os
+    import subprocess
+    import sys
+
+    code = (
+        "import numpy as np, sys; sys.path.insert(0, %r)\n"
+        "from cgp_b200.engine import ClusterGPEngine\n"
+        "rng = np.random.default_rng(3); n, d = 700, 3\n"
+        "X = rng.uniform(size=(n, d)); lab = (X[:, 0] > 0.4).astype(np.int64)\n"
+        "y = lab + np.sin(5 * X.sum(1)) + 0.03 * rng.standard_normal(n)\n"
+        "eng = ClusterGPEngine(X, y, lab, 'matern32', 1e-5)\n"
+        "th = rng.uniform(-1.2, 0.4, size=(6, d + 1)); th[:, d] = -4\n"
+        "lml, grad, info = eng.lml_grad(np.arange(6) %% 2, th, True)\n"
+        "eng.set_theta(th[:2]); m, s = eng.predict(rng.uniform(size=(300, d)))\n"
+        "print(lml.tobytes().hex(), grad.tobytes().hex(), m.cpu().numpy().tobytes().hex(), s.cpu().numpy().tobytes().hex())\n"
+    ) % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = []
+    for mode in ("big", "small", ""):
+        env = dict(os.environ, CGP_TILE_MODE=mode)
+        r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs.append(r.stdout.strip().splitlines()[-1])
+    assert outs[0] == outs[1] == outs[2]
