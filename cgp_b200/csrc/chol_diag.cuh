@@ -21,27 +21,34 @@ extern __shared__ __align__(16) double diag_smem[];
 // every index of the per-thread arrays is a compile-time constant: the arrays stay in registers and the
 // shared-memory operands (broadcast reads at static offsets) are hoisted out of the dependent FMA chains.
 
-// (1) one column step of the in-register 32x32 Cholesky (lane = row)
+// (1) one column step of the in-register 32x32 Cholesky (lane = row).  Software-pipelined: as soon as the first
+// trailing column has been updated, the pivot broadcast + rsqrt of the NEXT column are issued, so their latency hides
+// behind the remaining shuffle/FMA updates of this column.  (dcc, ip) = pivot of column C and its inverse square root.
 template <int C>
 struct FactorCol {
-    static __device__ __forceinline__ void run(double (&row)[32], int lane, int& failcol, double& dinv) {
-        const double dcc = __shfl_sync(0xffffffffu, row[C], C);
+    static __device__ __forceinline__ void run(double (&row)[32], int lane, int& failcol, double& dinv, double dcc, double ip) {
         if (!(dcc > 0.0) && failcol < 0) failcol = C;
-        const double ip = rsqrt(dcc);
         const double lc = (lane == C) ? dcc * ip : row[C] * ip;
         row[C] = lc;
         if (lane == C) dinv = ip;
+        double dnext = 0.0, ipnext = 0.0;
+        if (C + 1 < 32) {
+            const double lq = __shfl_sync(0xffffffffu, lc, C + 1);
+            if (lane >= C + 1) row[C + 1 < 32 ? C + 1 : 31] -= lc * lq;
+            dnext = __shfl_sync(0xffffffffu, row[C + 1 < 32 ? C + 1 : 31], C + 1 < 32 ? C + 1 : 31);
+            ipnext = rsqrt(dnext);
+        }
 #pragma unroll
-        for (int q = C + 1; q < 32; ++q) {
+        for (int q = C + 2; q < 32; ++q) {
             const double lq = __shfl_sync(0xffffffffu, lc, q);
             if (lane >= q) row[q] -= lc * lq;
         }
-        FactorCol<C + 1>::run(row, lane, failcol, dinv);
+        FactorCol<C + 1>::run(row, lane, failcol, dinv, dnext, ipnext);
     }
 };
 template <>
 struct FactorCol<32> {
-    static __device__ __forceinline__ void run(double (&)[32], int, int&, double&) {}
+    static __device__ __forceinline__ void run(double (&)[32], int, int&, double&, double, double) {}
 };
 
 // (2) forward substitution of one row against the 32x32 factor Lp (row stride DIAG_LD): x <- x Lp^-T
@@ -149,7 +156,8 @@ k_potrf_diag(double* __restrict__ Abuf, double* __restrict__ Ubuf, double* __res
             for (int q = 0; q < 32; ++q) row[q] = (q <= lane) ? S[(k0 + lane) * DIAG_LD + k0 + q] : 0.0;
             int failcol = -1;
             double dinv = 0.0;
-            FactorCol<0>::run(row, lane, failcol, dinv);
+            const double d0 = __shfl_sync(0xffffffffu, row[0], 0);
+            FactorCol<0>::run(row, lane, failcol, dinv, d0, rsqrt(d0));
 #pragma unroll
             for (int q = 0; q < 32; ++q) S[(k0 + lane) * DIAG_LD + k0 + q] = (q <= lane) ? row[q] : 0.0;
             rinv[k0 + lane] = dinv;
