@@ -457,8 +457,8 @@ extern "C" int cgp_lml_grad_batched(cgp_handle* hh, int kind, const double* X, c
     while (m0 < B) {
         int m1 = m0 + 1;
         if (batch_bytes(metas, m0, m1, d, true) > ws_bytes) return -16;
-        // grow geometrically then linearly
-        int lo = m1, hi = B;
+        // largest chunk that fits the workspace (bisection); gridDim.y carries the matrix index -> at most 65535
+        int lo = m1, hi = std::min(B, m0 + 65535);
         while (lo < hi) {
             int mid = (lo + hi + 1) / 2;
             if (batch_bytes(metas, m0, mid, d, true) <= ws_bytes) lo = mid; else hi = mid - 1;
@@ -536,6 +536,7 @@ extern "C" int cgp_factorize(cgp_handle* hh, int kind, const double* X, const do
     if (!workspace) return -15;
     cudaStream_t s = (cudaStream_t)stream;
     std::vector<MatMeta> metas;
+    if (C > 65535) return -5;
     cluster_metas(offs, C, metas);
     for (int c = 0; c < C; ++c)
         if (metas[c].n <= 0) return -5;

@@ -64,3 +64,32 @@ def test_knn_all_dims(d):
     for k in (1, 3, 5):
         got = _lib.knn_labels(torch.from_numpy(X).cuda(), torch.from_numpy(lab).cuda(), torch.from_numpy(Q).cuda(), k, C)
         assert np.array_equal(got.cpu().numpy(), oracle.knn_labels(X, lab, Q, k)), (d, k)
+
+
+def test_lml_over_full_bounds_range():
+    """Random thetas over the WHOLE optimiser box [log 1e-5, log 1e5]^P (where L-BFGS-B restarts are drawn): finite
+    values agree with LAPACK; where either side reports non-PD (ill-conditioned corners) both must be far from optimal."""
+    from cgp_b200.engine import ClusterGPEngine
+
+    rng = np.random.default_rng(77)
+    n, d = 200, 3
+    X = rng.uniform(size=(n, d))
+    y = np.sin(4 * X[:, 0]) + X[:, 1] - X[:, 2] ** 2 + 0.05 * rng.standard_normal(n)
+    eng = ClusterGPEngine(X, y, np.zeros(n, dtype=np.int64), "matern32", 1e-5)
+    yn, _, _ = oracle.normalize_y(y)
+    thetas = oracle.restart_thetas(d + 1, 60, seed=5)
+    lml, grad, info = eng.lml_grad(np.zeros(len(thetas), dtype=np.int32), thetas, True)
+    n_ok = 0
+    for i, th in enumerate(thetas):
+        l, g = oracle.lml_and_grad(X, yn, th, 1e-5, "matern32")
+        if info[i] == 0 and np.isfinite(l):
+            # conditioning: cond(K) <= n (1 + s2 + alpha) / (s2 + alpha); tolerance scales with it
+            s2 = np.exp(th[d])
+            cond = n * (1 + s2 + 1e-5) / (s2 + 1e-5)
+            tol = max(1e-8, 1e-14 * cond)
+            assert abs(lml[i] - l) <= tol * abs(l), (i, th, lml[i], l)
+            assert np.max(np.abs(grad[i] - g)) <= max(1e-6, 1e-12 * cond) * max(1.0, np.max(np.abs(g))), (i, th)
+            n_ok += 1
+        else:
+            assert (info[i] != 0 and lml[i] == -np.inf) or not np.isfinite(l)
+    assert n_ok >= 40
