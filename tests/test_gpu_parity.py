@@ -334,3 +334,62 @@ def test_return_cov_and_mspe_vs_reference():
         got = mean_square_prediction_error(X=Q[i], surrogate=m, X_sample=X, Y_sample=y.reshape(-1, 1),
                                            correct_label=np.float64(0), classify=clf, VERBOSE=False)
         assert abs(got - want) <= 1e-7 * abs(want)
+
+
+def test_workspace_hygiene_nan_fill_and_canaries(lib):
+    """compute-sanitizer is closed on this pool, so: (1) every workspace / output buffer is pre-filled with 0xFF bytes
+    (NaN as fp64, -1 as int) — a kernel that consumed uninitialised memory would propagate NaN into the results;
+    (2) a canary region behind each workspace must stay untouched (no out-of-bounds writes past the declared size)."""
+    rng = np.random.default_rng(21)
+    sizes = [37, 200, 300]
+    d, C = 4, 3
+    offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    n = int(offs[-1])
+    X = rng.uniform(size=(n, d))
+    lab_sorted = np.repeat(np.arange(C), sizes)
+    y = np.concatenate([oracle.normalize_y(np.sin(4 * X[offs[c]:offs[c + 1]].sum(1)) + 0.1 * rng.standard_normal(sizes[c]))[0]
+                        for c in range(C)])
+    pc = np.array([0, 1, 2, 1, 2], dtype=np.int32)
+    th = rng.uniform(-1, 0.5, size=(len(pc), d + 1))
+    th[:, d] = -3.0
+    CAN = 4096
+
+    def poisoned(nbytes):
+        t = torch.full((nbytes + CAN,), 0xFF, dtype=torch.uint8, device="cuda")
+        t[nbytes:] = 0xA5
+        return t
+
+    def canary_ok(t, nbytes):
+        return bool((t[nbytes:] == 0xA5).all())
+
+    need = lib.lml_workspace_bytes(offs, pc, d)
+    ws = poisoned(need)
+    Xd, yd, thd = dev(X), dev(y), dev(th)
+    lml, grad, info = lib.lml_grad_batched(Xd, yd, offs, pc, thd, 1e-5, "matern32", ws[:need])
+    assert canary_ok(ws, need)
+    lml, grad = lml.cpu().numpy(), grad.cpu().numpy()
+    assert np.all(np.isfinite(lml)) and np.all(np.isfinite(grad)) and np.all(info.cpu().numpy() == 0)
+    for i, c in enumerate(pc):
+        s = slice(offs[c], offs[c + 1])
+        l, g = oracle.lml_and_grad(X[s], y[s], th[i], 1e-5, "matern32")
+        assert abs(lml[i] - l) <= RTOL * abs(l) and np.max(np.abs(grad[i] - g)) <= 1e-7 * max(1.0, np.max(np.abs(g)))
+    # factorize + scoring with poisoned workspaces
+    need_f = lib.factorize_workspace_bytes(offs, d)
+    wf = poisoned(need_f)
+    m = lib.factorize(Xd, yd, offs, dev(th[:C]), 1e-5, "matern32", wf[:need_f])
+    assert canary_ok(wf, need_f) and np.all(np.isfinite(m["alpha_vec"].cpu().numpy()))
+    M = 1000
+    Q = rng.uniform(size=(M, d))
+    ql = dev(rng.integers(0, C, size=M), torch.int64)
+    need_s = lib.score_workspace_bytes(offs, d, M)
+    wsc = poisoned(need_s)
+    ones = dev(np.ones(C))
+    (bs, bi, bc), (score, mean, std) = lib.ei_argmax(Xd, offs, dev(th[:C]), m["W"], m["alpha_vec"], dev(np.zeros(C)), ones,
+                                                      dev(np.zeros(C)), dev(Q), ql, "matern32", 0, True, wsc[:need_s])
+    assert canary_ok(wsc, need_s)
+    sc = score.cpu().numpy()
+    assert np.all(np.isfinite(sc)) and np.all(np.isfinite(mean.cpu().numpy())) and np.all(std.cpu().numpy() >= 0)
+    assert int(bi.item()) == int(np.argmax(sc)) or sc[int(bi.item())] == sc.max()
+    (bs2, bi2, bc2), _ = lib.ei_argmax(Xd, offs, dev(th[:C]), m["W"], m["alpha_vec"], dev(np.zeros(C)), ones, dev(np.zeros(C)),
+                                        dev(Q), ql, "matern32", 0, False)
+    assert int(bi2.item()) == int(bi.item()) and float(bs2.item()) == float(bs.item())
