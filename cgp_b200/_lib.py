@@ -154,16 +154,23 @@ def lml_workspace_bytes(offs, pair_cluster, d):
     return int(lib().cgp_lml_workspace_bytes(po, len(o) - 1, ppc, len(pc), d))
 
 
-def lml_grad_batched(X, y, offs, pair_cluster, theta, alpha, kind, workspace, want_grad=True):
-    """theta [B,P] CUDA -> (lml [B], grad [B,P] | None, info [B]) CUDA tensors (asynchronous)."""
+def lml_grad_batched(X, y, offs, pair_cluster, theta, alpha, kind, workspace, want_grad=True, out=None):
+    """theta [B,P] CUDA -> (lml [B], grad [B,P] | None, info [B]) CUDA tensors (asynchronous).
+    `out` = (lml, grad, info) preallocated contiguous CUDA tensors of exactly these shapes (no allocation then)."""
     o, po = _host_i64(offs)
     pc, ppc = _host_i32(pair_cluster)
     B, P = theta.shape
     d = X.shape[1]
     assert P == d + 1 and len(pc) == B
-    lml = torch.empty(B, dtype=torch.float64, device=X.device)
-    grad = torch.empty((B, P), dtype=torch.float64, device=X.device) if want_grad else None
-    info = torch.empty(B, dtype=torch.int32, device=X.device)
+    if out is not None:
+        lml, grad, info = out
+        if not want_grad:
+            grad = None
+        assert lml.shape == (B,) and info.shape == (B,) and (grad is None or grad.shape == (B, P))
+    else:
+        lml = torch.empty(B, dtype=torch.float64, device=X.device)
+        grad = torch.empty((B, P), dtype=torch.float64, device=X.device) if want_grad else None
+        info = torch.empty(B, dtype=torch.int32, device=X.device)
     _chk(lib().cgp_lml_grad_batched(handle(X.device.index), KIND[kind], _ptr(X), _ptr(y), po, len(o) - 1, d, ppc, B,
                                     _ptr(theta), float(alpha), _ptr(lml), _ptr(grad), _ptr(info, torch.int32),
                                     _ptr(workspace, torch.uint8), workspace.numel(), _stream()),

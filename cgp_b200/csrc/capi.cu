@@ -48,10 +48,10 @@ struct HandleImpl : cgp_handle {
     double ms[CLS_COUNT];
     long long launches[CLS_COUNT];
     // second stream: the triangular-inverse chain of panel s runs beside the Cholesky chain of panel s+1
-    cudaStream_t s2;
+    cudaStream_t s2, sc;
     int tile_mode;  // 0 = by launch size, 1 = always 128x128 CTAs, 2 = always the small shapes
     std::vector<cudaEvent_t> panel_ev;
-    cudaEvent_t join_ev;
+    cudaEvent_t join_ev, start_ev, chain_ev;
 };
 
 static inline void prof_begin(HandleImpl* h, int cls, cudaStream_t s) {
@@ -116,7 +116,11 @@ extern "C" int cgp_create(cgp_handle** out, int device) {
         int lo = 0, hi = 0;
         CGP_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
         CGP_CHECK(cudaStreamCreateWithPriority(&h->s2, cudaStreamNonBlocking, lo));  // lowest priority: fills gaps
+        const char* pe = getenv("CGP_CHAIN_PRIO");  // "0": chain stream at default priority (measurement switch)
+        CGP_CHECK(cudaStreamCreateWithPriority(&h->sc, cudaStreamNonBlocking, (pe && pe[0] == '0') ? lo : hi));  // highest: the dependent chain
         CGP_CHECK(cudaEventCreateWithFlags(&h->join_ev, cudaEventDisableTiming));
+        CGP_CHECK(cudaEventCreateWithFlags(&h->start_ev, cudaEventDisableTiming));
+        CGP_CHECK(cudaEventCreateWithFlags(&h->chain_ev, cudaEventDisableTiming));
     }
     for (int i = 0; i < CLS_COUNT; ++i) h->ms[i] = 0.0, h->launches[i] = 0;
     CGP_CHECK(set_smem(k_dgemm_nt, GEMM_SMEM_BYTES));
@@ -128,6 +132,7 @@ extern "C" int cgp_create(cgp_handle** out, int device) {
     CGP_CHECK(set_smem(K<64, 128>, GEMM_SMEM_BYTES_T(64, 128)))
     SET3(k_potrf_update);
     SET3(k_potrf_trail);
+    SET3(k_potrf_head);
     SET3(k_trtri_acc);
     SET3(k_trtri_trail);
     SET3(k_lauum);
@@ -154,7 +159,10 @@ extern "C" int cgp_destroy(cgp_handle* hh) {
     }
     for (auto& e : h->panel_ev) cudaEventDestroy(e);
     cudaEventDestroy(h->join_ev);
+    cudaEventDestroy(h->start_ev);
+    cudaEventDestroy(h->chain_ev);
     cudaStreamDestroy(h->s2);
+    cudaStreamDestroy(h->sc);
     cudaEventDestroy(h->ring_event);
     cudaFreeHost(h->pinned);
     delete h;
@@ -303,32 +311,55 @@ static int run_pipeline(HandleImpl* h, int kind, const double* X, const double* 
         KL(h, CLS_ASSEMBLE, s, k_assemble<0><<<gl, 256, xs, s>>>(b.A, X, theta, b.meta, d, alpha));
     else
         KL(h, CLS_ASSEMBLE, s, k_assemble<1><<<gl, 256, xs, s>>>(b.A, X, theta, b.meta, d, alpha));
-    // Cholesky chain on the caller's stream; the triangular-inverse work of panel p only needs the Cholesky panel p
-    // (not its trailing update), so it is issued on a second stream behind an event and overlaps panel p+1.
+    // Three streams (when there is more than one panel):
+    //   sc  (high priority)  the latency-bound chain  update -> diag -> panel  of each block column, plus the part of the
+    //                        trailing update that the NEXT panel needs (k_potrf_head: look-ahead);
+    //   s   (caller)         the bulk of each trailing update (k_potrf_trail on the columns after the next panel);
+    //   s2  (low priority)   the triangular-inverse work of panel p, which only needs the Cholesky panel p.
+    // With few matrices in the batch (tail of the L-BFGS lock-step, small share per GPU) the chain leaves most SMs idle;
+    // the bulk and inverse launches of the same matrices fill them.  Every tile sees the same sequence of updates as in
+    // a single-stream schedule, so results are bit-identical.
     const int n_panels = (T + CGP_PANEL - 1) / CGP_PANEL;
     const bool fork = n_panels > 1;
     cudaStream_t st = fork ? h->s2 : s;
-    while ((int)h->panel_ev.size() < n_panels) {
+    cudaStream_t sc = fork ? h->sc : s;
+    while ((int)h->panel_ev.size() < 2 * n_panels) {
         cudaEvent_t e;
         CGP_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         h->panel_ev.push_back(e);
     }
+    if (fork) {
+        CGP_CHECK(cudaEventRecord(h->start_ev, s));
+        CGP_CHECK(cudaStreamWaitEvent(sc, h->start_ev, 0));
+    }
+    bool rest_pending = false;  // a bulk update whose result the next k_potrf_head must see
     for (int c0 = 0, p = 0; c0 < T; c0 += CGP_PANEL, ++p) {
         const int c1 = std::min(T, c0 + CGP_PANEL);
         for (int j = c0; j < c1; ++j) {
             if (j > c0)
-                GL(CLS_POTRF_UPDATE, s, k_potrf_update, T - j, nm, b.A, b.meta, j, c0);
-            KL(h, CLS_POTRF_DIAG, s, k_potrf_diag<<<nm, 256, DIAG_SMEM_BYTES, s>>>(b.A, b.U, b.D, b.logdet, info, b.meta, j, T));
+                GL(CLS_POTRF_UPDATE, sc, k_potrf_update, T - j, nm, b.A, b.meta, j, c0);
+            KL(h, CLS_POTRF_DIAG, sc, k_potrf_diag<<<nm, 256, DIAG_SMEM_BYTES, sc>>>(b.A, b.U, b.D, b.logdet, info, b.meta, j, T));
             if (j + 1 < T)
-                GLI(CLS_POTRF_PANEL, s, k_potrf_panel, T - j - 1, nm, b.A, b.D, b.meta, j);
+                GLI(CLS_POTRF_PANEL, sc, k_potrf_panel, T - j - 1, nm, b.A, b.D, b.meta, j);
         }
         if (fork) {
-            CGP_CHECK(cudaEventRecord(h->panel_ev[p], s));
-            CGP_CHECK(cudaStreamWaitEvent(st, h->panel_ev[p], 0));
+            CGP_CHECK(cudaEventRecord(h->panel_ev[2 * p], sc));
+            CGP_CHECK(cudaStreamWaitEvent(st, h->panel_ev[2 * p], 0));
         }
         if (c1 < T) {
-            const int Tt = T - c1;
-            GL(CLS_POTRF_TRAIL, s, k_potrf_trail, Tt * (Tt + 1) / 2, nm, b.A, b.meta, c0, c1);
+            const int H = std::min(CGP_PANEL, T - c1);
+            if (fork && rest_pending) CGP_CHECK(cudaStreamWaitEvent(sc, h->panel_ev[2 * (p - 1) + 1], 0));
+            rest_pending = false;
+            GL(CLS_POTRF_TRAIL, sc, k_potrf_head, H * (T - c1), nm, b.A, b.meta, c0, c1, T);
+            const int Tr = T - c1 - H;
+            if (Tr > 0) {
+                if (fork) CGP_CHECK(cudaStreamWaitEvent(s, h->panel_ev[2 * p], 0));
+                GL(CLS_POTRF_TRAIL, s, k_potrf_trail, Tr * (Tr + 1) / 2, nm, b.A, b.meta, c0, c1, c1 + H);
+                if (fork) {
+                    CGP_CHECK(cudaEventRecord(h->panel_ev[2 * p + 1], s));
+                    rest_pending = true;
+                }
+            }
         }
         for (int i = std::max(c0, 1); i < c1; ++i) {
             if (i > c0)
@@ -339,6 +370,8 @@ static int run_pipeline(HandleImpl* h, int kind, const double* X, const double* 
             GL(CLS_TRTRI_TRAIL, st, k_trtri_trail, c1 * (T - c1), nm, b.A, b.U, b.meta, c0, c1, T);
     }
     if (fork) {
+        CGP_CHECK(cudaEventRecord(h->chain_ev, sc));
+        CGP_CHECK(cudaStreamWaitEvent(s, h->chain_ev, 0));
         CGP_CHECK(cudaEventRecord(h->join_ev, st));
         CGP_CHECK(cudaStreamWaitEvent(s, h->join_ev, 0));
     }

@@ -216,11 +216,13 @@ k_potrf_update(double* __restrict__ Abuf, const MatMeta* __restrict__ meta, int 
                          A + (long long)i * CGP_TILE * ld + (long long)j * CGP_TILE, ld, blockIdx.x % GEMM_PIECES(BM, BN));
 }
 
-// Trailing update after panel [c0, c1):  A[i,k] -= sum_{c=c0}^{c1-1} L[i,c] L[k,c]^T  for c1 <= k <= i < T.
-// tiles: Tt(Tt+1)/2 with Tt = Tmax - c1
+// Trailing update after panel [c0, c1):  A[i,k] -= sum_{c=c0}^{c1-1} L[i,c] L[k,c]^T  for t0 <= k <= i < T  (t0 >= c1).
+// tiles: Tt(Tt+1)/2 with Tt = Tmax - t0.  The update is issued in two launches (look-ahead): the block columns of the
+// NEXT panel first (k_potrf_head, on the critical path of the factorisation), the rest (this kernel, t0 = start of
+// the panel after next) on a bulk stream where it overlaps the latency-bound diag/panel chain of the next panel.
 template <int BM, int BN>
 __global__ void GEMM_BOUNDS(BM, BN)
-k_potrf_trail(double* __restrict__ Abuf, const MatMeta* __restrict__ meta, int c0, int c1) {
+k_potrf_trail(double* __restrict__ Abuf, const MatMeta* __restrict__ meta, int c0, int c1, int t0) {
     const MatMeta m = meta[blockIdx.y];
     const int T = m.npad / CGP_TILE;
     int idx = blockIdx.x / GEMM_PIECES(BM, BN), a = 0;
@@ -228,7 +230,25 @@ k_potrf_trail(double* __restrict__ Abuf, const MatMeta* __restrict__ meta, int c
         idx -= a + 1;
         ++a;
     }
-    const int i = c1 + a, k = c1 + idx;
+    const int i = t0 + a, k = t0 + idx;
+    if (i >= T) return;
+    double* A = Abuf + m.a_off;
+    const long long ld = m.npad;
+    gemm_tile<2, BM, BN>(A + (long long)i * CGP_TILE * ld + (long long)c0 * CGP_TILE, ld,
+                         A + (long long)k * CGP_TILE * ld + (long long)c0 * CGP_TILE, ld, (c1 - c0) * CGP_TILE,
+                         A + (long long)i * CGP_TILE * ld + (long long)k * CGP_TILE, ld, blockIdx.x % GEMM_PIECES(BM, BN));
+}
+
+// Same update restricted to the block columns k in [c1, c1 + H) (the next panel), rows i >= k.
+// tiles: H * (Tmax - c1), tile = q * (Tmax - c1) + r  ->  k = c1 + q, i = k + r
+template <int BM, int BN>
+__global__ void GEMM_BOUNDS(BM, BN)
+k_potrf_head(double* __restrict__ Abuf, const MatMeta* __restrict__ meta, int c0, int c1, int Tmax) {
+    const MatMeta m = meta[blockIdx.y];
+    const int T = m.npad / CGP_TILE;
+    const int w = Tmax - c1;
+    const int tile = blockIdx.x / GEMM_PIECES(BM, BN);
+    const int k = c1 + tile / w, i = k + tile % w;
     if (i >= T) return;
     double* A = Abuf + m.a_off;
     const long long ld = m.npad;

@@ -6,6 +6,7 @@ over ranks.  No CPU fallback.
 """
 from __future__ import annotations
 
+import gc
 import math
 import os
 import time
@@ -91,50 +92,82 @@ class ClusterGPEngine:
         self.theta = None
         self.model = None
         self._ws = None
+        self._ws_capped = False
+        self._slots = []
         self.fit_stats = {}
 
     # ------------------------------------------------------------------ workspace
-    def _workspace(self, nbytes):
-        free, _total = torch.cuda.mem_get_info(self.device)
+    def _workspace(self, nbytes, partial_ok=False):
+        """Grow-only scratch buffer.  partial_ok: the caller (batched LML) can work in chunks with less than nbytes."""
         have = 0 if self._ws is None else self._ws.numel()
-        if have >= nbytes:
+        if have >= nbytes or (partial_ok and self._ws_capped and have > 0):
             return self._ws
+        # cudaMemGetInfo is slow (measured: up to 59 ms per call on a busy B200) -> only when the workspace must grow
+        free, _total = torch.cuda.mem_get_info(self.device)
         budget = int((free + have) * self.mem_fraction)
         want = min(nbytes, budget)
         if want > have:
             self._ws = None
             self._ws = torch.empty(want, dtype=torch.uint8, device=self.device)
+        self._ws_capped = partial_ok and want < nbytes  # at the memory budget: the C-ABI chunks the batch; do not ask again this fit
         return self._ws
 
     # ------------------------------------------------------------------ LML
+    def _eval_slot(self, B):
+        """A free set of persistent evaluation buffers (device theta/lml/grad/info + pinned host mirrors) holding at
+        least B pairs.  Lock-steps reuse them, so the steady state of a fit allocates nothing (pinned allocations and
+        device mallocs cost milliseconds and showed up as 5-50 ms spikes in the host part of small-matrix fits)."""
+        for slot in self._slots:
+            if not slot["busy"] and slot["cap"] >= B:
+                return slot
+        cap = 1
+        while cap < B:
+            cap *= 2
+        dev, P = self.device, self.P
+        slot = dict(cap=cap, busy=False, ev=torch.cuda.Event(),
+                    th=torch.empty((cap, P), dtype=torch.float64, device=dev),
+                    lml=torch.empty(cap, dtype=torch.float64, device=dev),
+                    grad=torch.empty((cap, P), dtype=torch.float64, device=dev),
+                    info=torch.empty(cap, dtype=torch.int32, device=dev),
+                    th_h=torch.empty((cap, P), dtype=torch.float64, pin_memory=True),
+                    lml_h=torch.empty(cap, dtype=torch.float64, pin_memory=True),
+                    grad_h=torch.empty((cap, P), dtype=torch.float64, pin_memory=True),
+                    info_h=torch.empty(cap, dtype=torch.int32, pin_memory=True))
+        self._slots = [s for s in self._slots if s["busy"] or s["cap"] >= cap] + [slot]  # drop outgrown free slots
+        return slot
+
     def lml_grad_submit(self, pair_cluster, thetas, want_grad=True):
         """Enqueue a batched LML (+ gradient) evaluation and the device->pinned-host copies of its results.
         Returns a ticket for lml_grad_collect; nothing here waits for the device."""
         pair_cluster = np.asarray(pair_cluster, dtype=np.int32)
-        thetas = np.ascontiguousarray(np.asarray(thetas, dtype=np.float64).reshape(len(pair_cluster), self.P))
+        B = len(pair_cluster)
+        thetas = np.asarray(thetas, dtype=np.float64).reshape(B, self.P)
         need = _lib.lml_workspace_bytes(self.offs, pair_cluster, self.d)
-        ws = self._workspace(need)
-        th = torch.from_numpy(thetas).to(self.device, non_blocking=True)
-        lml, grad, info = _lib.lml_grad_batched(self.Xs, self.yn, self.offs, pair_cluster, th, self.alpha, self.kind,
-                                                ws, want_grad)
-        host = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True) if t is not None else None for t in (lml, grad, info)]
-        for h, t in zip(host, (lml, grad, info)):
-            if t is not None:
-                h.copy_(t, non_blocking=True)
-        ev = torch.cuda.Event()
-        ev.record()
-        return host, ev, (th, lml, grad, info)  # device tensors are kept alive until collected
+        ws = self._workspace(need, partial_ok=True)
+        slot = self._eval_slot(B)
+        slot["busy"] = True
+        slot["th_h"].numpy()[:B] = thetas
+        th = slot["th"][:B]
+        th.copy_(slot["th_h"][:B], non_blocking=True)
+        out = (slot["lml"][:B], slot["grad"][:B], slot["info"][:B])
+        _lib.lml_grad_batched(self.Xs, self.yn, self.offs, pair_cluster, th, self.alpha, self.kind, ws, want_grad, out=out)
+        slot["lml_h"][:B].copy_(out[0], non_blocking=True)
+        if want_grad:
+            slot["grad_h"][:B].copy_(out[1], non_blocking=True)
+        slot["info_h"][:B].copy_(out[2], non_blocking=True)
+        slot["ev"].record()
+        return slot, B, want_grad
 
     def lml_grad_collect(self, ticket):
         """-> (lml, grad | None, info) host arrays; non-PD -> (-inf, 0) as SK/_gpr.py:592-593."""
-        host, ev, _keep = ticket
-        ev.synchronize()
-        lml, info = host[0].numpy().copy(), host[2].numpy().copy()
+        slot, B, want_grad = ticket
+        slot["ev"].synchronize()
+        lml, info = slot["lml_h"].numpy()[:B].copy(), slot["info_h"].numpy()[:B].copy()
+        grad = slot["grad_h"].numpy()[:B].copy() if want_grad else None
+        slot["busy"] = False
         bad = info != 0
         lml[bad] = -np.inf
-        grad = None
-        if host[1] is not None:
-            grad = host[1].numpy().copy()
+        if grad is not None:
             grad[bad] = 0.0
         return lml, grad, info
 
@@ -154,6 +187,7 @@ class ClusterGPEngine:
             shard_mode = os.environ.get("CGP_SHARD_MODE", "static")  # measured on 8 B200: balanced 3.19 s/step, static 3.24
         rank, ws = cdist.world()
         P, C = self.P, self.C
+        self._ws_capped = False
         lo = np.full(P, LOG_LO) if bounds is None else np.asarray(bounds, float)[:, 0]
         hi = np.full(P, LOG_HI) if bounds is None else np.asarray(bounds, float)[:, 1]
         starts = restart_thetas(P, n_restarts, seed, lo, hi)
@@ -201,9 +235,15 @@ class ClusterGPEngine:
                 return t.cpu().numpy()
 
             shard = dict(rank=rank, world=ws, cost=self.counts[pc_all].astype(np.float64) ** 3, allreduce=allreduce)
-        xs, fs, nfev, nit, steps = minimize_lockstep(eval_batch, x0s, lo, hi, submit=submit, collect=collect,
-                                                     pipeline_min=int(os.environ.get("CGP_PIPELINE_MIN", "256")),
-                                                     shard=shard)
+        gc_was_on = gc.isenabled()
+        gc.disable()  # thousands of live L-BFGS-B machines: a generation-2 sweep inside a lock-step costs tens of ms
+        try:
+            xs, fs, nfev, nit, steps = minimize_lockstep(eval_batch, x0s, lo, hi, submit=submit, collect=collect,
+                                                         pipeline_min=int(os.environ.get("CGP_PIPELINE_MIN", "256")),
+                                                         shard=shard)
+        finally:
+            if gc_was_on:
+                gc.enable()
         t_opt = time.perf_counter() - t_fit0
         rows = np.concatenate([xs, fs[:, None]], axis=1).reshape(len(mine), P + 1)
         if balanced:  # every rank already holds every run's result
