@@ -41,6 +41,9 @@ SIGNATURES = {
                               _vp, _vp, _vp, _sz, _vp]),
     "cgp_ei_argmax": (C.c_int, [_vp, C.c_int, _vp, _pi64, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                 _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "cgp_append_workspace_bytes": (_sz, [_i64]),
+    "cgp_append_sample": (C.c_int, [_vp, C.c_int, _vp, _i64, C.c_int, _vp, _f64, _vp, _vp, _i64, _vp, _vp, _sz, _vp]),
+    "cgp_refresh_alpha": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _sz, _vp]),
     "cgp_dgemm_nt": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp]),
     "cgp_profile_classes": (C.c_int, []),
     "cgp_profile_class_name": (C.c_char_p, [C.c_int]),
@@ -201,6 +204,31 @@ def factorize(X, y, offs, theta, alpha, kind, workspace=None):
                              _ptr(L), _ptr(W), _ptr(av), _ptr(lml), _ptr(info, torch.int32),
                              _ptr(workspace, torch.uint8), workspace.numel(), _stream()), "cgp_factorize")
     return dict(L=L, W=W, alpha_vec=av, lml=lml, info=info)
+
+
+def append_workspace_bytes(n_new):
+    return int(lib().cgp_append_workspace_bytes(int(n_new)))
+
+
+def append_sample(Xc, theta_c, alpha, kind, L_c, W_c, workspace):
+    """Extend the factor blocks L_c / W_c ([npad, npad] views, old factor in the leading block) by the LAST row of Xc.
+    -> info (1-element int32 CUDA tensor)."""
+    n_new, d = Xc.shape
+    npad = L_c.shape[0]
+    info = torch.empty(1, dtype=torch.int32, device=Xc.device)
+    _chk(lib().cgp_append_sample(handle(Xc.device.index), KIND[kind], _ptr(Xc), n_new, d, _ptr(theta_c), float(alpha),
+                                 _ptr(L_c), _ptr(W_c), npad, _ptr(info, torch.int32), _ptr(workspace, torch.uint8),
+                                 workspace.numel(), _stream()), "cgp_append_sample")
+    return info
+
+
+def refresh_alpha(L_c, W_c, n, y_c, alpha_out, workspace):
+    """alpha_out[:n] = K^-1 y_c for one factorised cluster; -> lml (1-element CUDA tensor)."""
+    lml = torch.empty(1, dtype=torch.float64, device=y_c.device)
+    _chk(lib().cgp_refresh_alpha(handle(y_c.device.index), _ptr(L_c), _ptr(W_c), L_c.shape[0], int(n), _ptr(y_c),
+                                 _ptr(alpha_out), _ptr(lml), _ptr(workspace, torch.uint8), workspace.numel(), _stream()),
+         "cgp_refresh_alpha")
+    return lml
 
 
 def knn_labels(X, labels, Q, k, n_classes):

@@ -35,10 +35,25 @@ class CGPRegressor:
         eng.fit(R, seed=self.random_state, theta0=theta0, bounds=bounds, optimize=self.optimizer is not None)
         self.engine_ = eng
         self._template = template
+        self._bounds = bounds
         self.n_clusters_ = eng.C
         self.theta_ = eng.theta.copy()
         self.log_marginal_likelihood_value_ = eng.model["lml_host"].copy()
         self.classify_ = KNeighborsClassifier(n_neighbors=min(self.n_neighbors, X.shape[0])).fit(X, labels)
+        self._gpr_list = None
+        return self
+
+    def partial_fit(self, x, y, label, reoptimize=False, n_restarts=0):
+        """Incremental refit: add one sample to cluster `label`.  With reoptimize=False theta stays
+        and only that cluster's factor grows by a row (exact: equals refactorising the extended data at the same theta);
+        with reoptimize=True every cluster is re-optimised starting from its current theta (+ n_restarts random starts)."""
+        eng = self.engine_
+        eng.append(x, y, label)
+        if reoptimize and self.optimizer is not None:
+            eng.fit(int(n_restarts), seed=self.random_state, theta0=eng.theta, bounds=self._bounds)
+        self.theta_ = eng.theta.copy()
+        self.log_marginal_likelihood_value_ = eng.model["lml_host"].copy()
+        self.classify_ = KNeighborsClassifier(n_neighbors=min(self.n_neighbors, eng.n)).fit(eng.X_host, eng.labels_host)
         self._gpr_list = None
         return self
 

@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "../../include/cgp_b200.h"
+#include "append.cuh"
 #include "chol_diag.cuh"
 #include "common.cuh"
 #include "gemm_nt.cuh"
@@ -25,13 +26,13 @@ enum {
     CLS_ASSEMBLE, CLS_POTRF_UPDATE, CLS_POTRF_TRAIL, CLS_POTRF_DIAG, CLS_POTRF_PANEL, CLS_TRTRI_ACC, CLS_TRTRI_TRAIL,
     CLS_TRTRI_SCALE, CLS_SOLVE,
     CLS_LAUUM, CLS_GRAD, CLS_TRANSPOSE, CLS_KNN, CLS_BUCKET, CLS_CROSS, CLS_MEAN, CLS_PREDICT_VNORM,
-    CLS_SCORE_FINISH, CLS_ARGMAX, CLS_DGEMM, CLS_COUNT
+    CLS_SCORE_FINISH, CLS_ARGMAX, CLS_DGEMM, CLS_APPEND, CLS_COUNT
 };
 static const char* const kClassNames[CLS_COUNT] = {
     "assemble", "potrf_update", "potrf_trail", "potrf_diag", "potrf_panel", "trtri_acc", "trtri_trail",
     "trtri_scale", "solve_lml",
     "lauum", "grad", "transpose", "knn", "bucket", "cross", "mean", "predict_vnorm",
-    "score_finish", "argmax", "dgemm_nt"};
+    "score_finish", "argmax", "dgemm_nt", "append"};
 
 struct ProfRec {
     cudaEvent_t a, b;
@@ -586,6 +587,104 @@ extern "C" int cgp_factorize(cgp_handle* hh, int kind, const double* X, const do
     if (rc) return rc;
     KL(h, CLS_TRANSPOSE, s, k_transpose<<<dim3(b.npad_max / 32, b.npad_max / 32, C), dim3(32, 8), 0, s>>>(b.U, W, b.meta));
     KL(h, CLS_SOLVE, s, k_gather_alpha<<<dim3((b.npad_max + 255) / 256, C), 256, 0, s>>>(b.a, alpha_vec, b.meta, b.npad_max));
+    return (int)cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// incremental refit: rank-1 append to one cluster (append.cuh)
+// ------------------------------------------------------------------------------------------------
+struct AppendLayout {
+    int64_t npad;
+    int nch;
+    size_t o_k, o_l, o_dd, o_part, total;
+};
+static AppendLayout append_layout(int64_t n) {
+    AppendLayout A;
+    A.npad = pad_n(std::max<int64_t>(n, 1));
+    A.nch = (int)((A.npad + APP_CH - 1) / APP_CH);
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        size_t o = off;
+        off = align_up(off + bytes, 256);
+        return o;
+    };
+    A.o_k = take((size_t)A.npad * 8);
+    A.o_l = take((size_t)A.npad * 8);
+    A.o_dd = take(8);
+    A.o_part = take((size_t)A.nch * A.npad * 8);
+    A.total = off;
+    return A;
+}
+
+extern "C" size_t cgp_append_workspace_bytes(int64_t n_new) {
+    if (n_new <= 0) return 0;
+    return append_layout(n_new).total;
+}
+
+// out = W^T x over the leading n x n lower block (two launches, fixed summation order)
+static void launch_tmatvec(HandleImpl* h, const double* W, int64_t ld, int n, const double* x, double* part, int64_t pstride,
+                           const double* scale_ptr, double* out, int64_t ostride, cudaStream_t s) {
+    dim3 g((unsigned)((n + 127) / 128), (unsigned)((n + APP_CH - 1) / APP_CH));
+    KL(h, CLS_APPEND, s, k_lower_tmatvec_part<<<g, 128, 0, s>>>(W, ld, n, x, part, (int)pstride));
+    KL(h, CLS_APPEND, s, k_lower_tmatvec_fin<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(part, (int)pstride, n, scale_ptr, out, ostride));
+}
+
+extern "C" int cgp_append_sample(cgp_handle* hh, int kind, const double* Xc, int64_t n_new, int d, const double* theta,
+                                 double alpha, double* L, double* W, int64_t npad, int32_t* info, void* workspace,
+                                 size_t ws_bytes, void* stream) {
+    HandleImpl* h = static_cast<HandleImpl*>(hh);
+    if (!h) return -1;
+    if (kind != 0 && kind != 1) return -2;
+    if (!Xc) return -3;
+    if (n_new < 1 || n_new > 0x7fffffff) return -4;
+    if (d < 1 || d > CGP_MAX_D) return -5;
+    if (!theta) return -6;
+    if (!L) return -8;
+    if (!W) return -9;
+    if (npad != pad_n(n_new)) return -10;
+    if (!info) return -11;
+    if (!workspace) return -12;
+    AppendLayout A = append_layout(n_new);
+    if (A.total > ws_bytes) return -13;
+    cudaStream_t s = (cudaStream_t)stream;
+    char* ws = static_cast<char*>(workspace);
+    double* kv = reinterpret_cast<double*>(ws + A.o_k);
+    double* lv = reinterpret_cast<double*>(ws + A.o_l);
+    double* dd = reinterpret_cast<double*>(ws + A.o_dd);
+    double* part = reinterpret_cast<double*>(ws + A.o_part);
+    const int n = (int)(n_new - 1);  // old sample count = index of the new row
+    CGP_CHECK(cudaMemsetAsync(info, 0, sizeof(int32_t), s));
+    if (n > 0) {
+        // k = k(x_new, X_old): one row of the cross kernel (no White term off the diagonal)
+        int rc = launch_cross(h, kind, Xc + (long long)n * d, 1, Xc, n, d, theta, kv, n, 1, n, 0, 0.0, s);
+        if (rc) return rc;
+        KL(h, CLS_APPEND, s, k_lower_matvec<<<(unsigned)((n + 7) / 8), 256, 0, s>>>(W, npad, n, kv, lv));
+    }
+    KL(h, CLS_APPEND, s, k_append_finish<<<1, 256, 0, s>>>(L, W, npad, n, lv, theta, d, alpha, dd, info));
+    if (n > 0) launch_tmatvec(h, W, npad, n, lv, part, A.npad, dd, W + (long long)n * npad, 1, s);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int cgp_refresh_alpha(cgp_handle* hh, const double* L, const double* W, int64_t npad, int64_t n, const double* y,
+                                 double* alpha_out, double* lml, void* workspace, size_t ws_bytes, void* stream) {
+    HandleImpl* h = static_cast<HandleImpl*>(hh);
+    if (!h) return -1;
+    if (!L) return -2;
+    if (!W) return -3;
+    if (n < 1 || n > 0x7fffffff || npad != pad_n(n)) return -5;
+    if (!y) return -6;
+    if (!alpha_out) return -7;
+    if (!lml) return -8;
+    if (!workspace) return -9;
+    AppendLayout A = append_layout(n);
+    if (A.total > ws_bytes) return -10;
+    cudaStream_t s = (cudaStream_t)stream;
+    char* ws = static_cast<char*>(workspace);
+    double* z = reinterpret_cast<double*>(ws + A.o_l);
+    double* part = reinterpret_cast<double*>(ws + A.o_part);
+    KL(h, CLS_APPEND, s, k_lower_matvec<<<(unsigned)((n + 7) / 8), 256, 0, s>>>(W, npad, (int)n, y, z));
+    launch_tmatvec(h, W, npad, (int)n, z, part, A.npad, nullptr, alpha_out, 1, s);
+    KL(h, CLS_APPEND, s, k_lml_from_factor<<<1, 256, 0, s>>>(L, npad, (int)n, z, lml));
     return (int)cudaGetLastError();
 }
 

@@ -40,6 +40,9 @@ class cGP_constrained(object):
         # additions of the GPU backend: size of the dense candidate scan and restart count (default 10*d, :412-413)
         self.N_CANDIDATES = g("N_CANDIDATES_CGP", 65536)
         self.N_RESTARTS = g("N_RESTARTS_CGP", None)
+        # incremental refit: when the clustering keeps the labels of the old samples, append the
+        # new sample to its cluster and re-optimise from the previous theta instead of refitting from scratch
+        self.INCREMENTAL = g("INCREMENTAL_CGP", False)
         self.PILOT_SAMPLES = g("PILOT_SAMPLES_CGP", None)
         self.OUTPUT_NAME = g("OUTPUT_NAME_CGP", None)
         self.OBJ_NAME = g("OBJ_NAME_CGP", None)
@@ -141,16 +144,26 @@ class cGP_constrained(object):
             Y[k, 0] = self.censor_function(self.f_truth(X[k, :].reshape(1, -1)))
         dgm = self.f_Cluster(self.RND_SEED)
         model, labels = None, None
+        fitted_n, fitted_labels = 0, None  # what `model` currently holds
         self.history = []
         for it in range(self.N_SEQUENTIAL):
             labels = self._labels(X, Y, dgm)
             coin = np.random.uniform(0, 1, 1)
             if coin < self.EXPLORATION_RATE:
                 R = 10 * d if self.N_RESTARTS is None else int(self.N_RESTARTS)
-                model = CGPRegressor(kernel=self.get_kernel(d), alpha=self.ALPHA_SKLEARN, n_restarts_optimizer=R,
-                                     normalize_y=self.SKLEARN_normalizer, random_state=0,
-                                     n_neighbors=min(self.N_NEIGHBORS, X.shape[0]))
-                model.fit(X, Y.reshape(-1), labels)
+                n = X.shape[0]
+                if (self.INCREMENTAL and model is not None and fitted_n < n and int(labels.max()) + 1 == model.n_clusters_
+                        and np.array_equal(labels[:fitted_n], fitted_labels)):
+                    for k in range(fitted_n, n):  # samples drawn since the last fit (random-search steps included)
+                        model.partial_fit(X[k], Y[k, 0], labels[k], reoptimize=(k == n - 1), n_restarts=0)
+                    mode = "acquisition+incremental"
+                else:
+                    model = CGPRegressor(kernel=self.get_kernel(d), alpha=self.ALPHA_SKLEARN, n_restarts_optimizer=R,
+                                         normalize_y=self.SKLEARN_normalizer, random_state=0,
+                                         n_neighbors=min(self.N_NEIGHBORS, X.shape[0]))
+                    model.fit(X, Y.reshape(-1), labels)
+                    mode = "acquisition"
+                fitted_n, fitted_labels = n, labels.copy()
                 Q = self._candidates(bounds)
                 pen = self.boundary_penalty(Q, X)
                 if np.isscalar(pen) and pen == 0:
@@ -162,7 +175,7 @@ class cGP_constrained(object):
                     order = np.lexsort((np.arange(sc.shape[0]), out["labels"], -sc))
                     idx = int(order[0])
                     X_next, score = Q[idx], float(sc[idx])
-                self.history.append(dict(step=it, mode="acquisition", score=float(score), n_clusters=int(labels.max()) + 1))
+                self.history.append(dict(step=it, mode=mode, score=float(score), n_clusters=int(labels.max()) + 1))
             else:  # random search inside the bounds (:380-412)
                 X_next = np.random.uniform(bounds[:, 0], bounds[:, 1])
                 while not self.REPEAT_SAMPLE and np.any(np.all(X == X_next[None, :], axis=1)):
@@ -236,6 +249,7 @@ def main(argv=None):
     p.add_option("-X", "--QUIET", action="store_true", dest="QUIET")
     p.add_option("--candidates", type="int", dest="CANDIDATES", default=65536)
     p.add_option("--restarts", type="int", dest="RESTARTS", default=None)
+    p.add_option("--incremental", action="store_true", dest="INCREMENTAL", default=False)
     o, _ = p.parse_args(argv)
     if o.N_SEQUENTIAL is None:
         raise Exception("ERROR: N_SEQEUNTIAL(int) is a compulsory parameter that must be supplied. \n e.g. -s 20")
@@ -280,7 +294,7 @@ def main(argv=None):
     run = Run({"N_PILOT_CGP": o.N_PILOT, "N_SEQUENTIAL_CGP": o.N_SEQUENTIAL, "RND_SEED_CGP": o.RND_SEED,
                "EXAMPLE_NAME_CGP": name, "EXPLORATION_RATE_CGP": o.EXPLORATION_RATE, "NO_CLUSTER_CGP": bool(o.NO_CLUSTER),
                "N_NEIGHBORS_CGP": o.N_NEIGHBORS, "N_COMPONENTS_CGP": o.N_COMPONENT, "N_CANDIDATES_CGP": o.CANDIDATES,
-               "N_RESTARTS_CGP": o.RESTARTS, "PILOT_SAMPLES_CGP": o.PILOT_FILE, "OUTPUT_NAME_CGP": out,
+               "N_RESTARTS_CGP": o.RESTARTS, "INCREMENTAL_CGP": o.INCREMENTAL, "PILOT_SAMPLES_CGP": o.PILOT_FILE, "OUTPUT_NAME_CGP": out,
                "OBJ_NAME_CGP": o.OBJ_NAME, "VERBOSE_CGP": not o.QUIET})
     X, Y = run.run()
     if not o.QUIET:

@@ -51,6 +51,7 @@ class ClusterGPEngine:
             raise ValueError("X [n,d], y [n], labels [n] expected")
         self.kind = kind
         self.alpha = float(alpha)
+        self._normalize_y = bool(normalize_y)
         self.n, self.d = X.shape
         self.P = self.d + 1
         self.C = int(labels.max()) + 1
@@ -180,29 +181,37 @@ class ClusterGPEngine:
         """All clusters x (R+1) restarts in lock-step (SK/_gpr.py:296-340), sharded over ranks, then the final
         factorisation at each cluster's best theta (SK/_gpr.py:349-367).
 
-        shard_mode "static": the (cluster, restart) pairs are dealt round-robin once; each rank optimises its own pairs
-        and one all-gather of (theta*, -lml) rows follows.  "balanced": every rank keeps all state machines and in each
-        lock-step evaluates only its share of the waiting runs (see lbfgs.minimize_lockstep)."""
+        shard_mode "balanced" (default): every rank keeps all state machines and in each lock-step evaluates only its
+        share of the waiting runs, one all-reduce of (f, g) per lock-step (see lbfgs.minimize_lockstep); the work stays
+        even although run lengths range from 2 to 167 evaluations.  "static": the (cluster, restart) pairs are dealt
+        round-robin once, each rank optimises its own pairs, one all-gather of (theta*, -lml) rows follows.
+        Measured on 8 B200, config 3: balanced 2.62 s / iteration, static 2.70 s (its slowest rank draws 754 of the 4938
+        evaluations, mean 617).  Both select the same point with the same score bits."""
         if shard_mode is None:
-            shard_mode = os.environ.get("CGP_SHARD_MODE", "static")  # measured on 8 B200: balanced 3.19 s/step, static 3.24
+            shard_mode = os.environ.get("CGP_SHARD_MODE", "balanced")
         rank, ws = cdist.world()
         P, C = self.P, self.C
         self._ws_capped = False
         lo = np.full(P, LOG_LO) if bounds is None else np.asarray(bounds, float)[:, 0]
         hi = np.full(P, LOG_HI) if bounds is None else np.asarray(bounds, float)[:, 1]
         starts = restart_thetas(P, n_restarts, seed, lo, hi)
+        start0 = None  # per-cluster start of run 0 (warm start from a previous fit), else the same theta0 everywhere
         if theta0 is not None:
-            starts[0] = np.asarray(theta0, float)
+            theta0 = np.asarray(theta0, float)
+            if theta0.ndim == 2:
+                start0 = np.clip(theta0.reshape(C, P), lo, hi)
+            else:
+                starts[0] = theta0
         R1 = starts.shape[0]
         if not optimize:
-            self.theta = np.tile(starts[0], (C, 1))
+            self.theta = np.tile(starts[0], (C, 1)) if start0 is None else start0.copy()
             self._factorize()
             return self
         n_pairs = C * R1  # pair p = (cluster p // R1, run p % R1)
         balanced = ws > 1 and shard_mode == "balanced"
         mine = list(range(n_pairs)) if balanced else cdist.my_pairs(n_pairs, rank, ws)
         pc_all = np.asarray([p // R1 for p in mine], dtype=np.int32)
-        x0s = [starts[p % R1] for p in mine]
+        x0s = [starts[p % R1] if (start0 is None or p % R1) else start0[p // R1] for p in mine]
         n_eval = [0]
         t_eval = [0.0]
         evals_c = np.zeros(C, dtype=np.int64)  # evaluations THIS rank performed, per cluster
@@ -286,6 +295,88 @@ class ClusterGPEngine:
         npad = [_lib.padded_n(int(c)) for c in self.counts]
         self.npad = np.asarray(npad, dtype=np.int64)
         self.moff = np.concatenate([[0], np.cumsum(self.npad * self.npad)]).astype(np.int64)
+
+    # ------------------------------------------------------------------ incremental refit
+    def append(self, x, y, label):
+        """Add ONE sample to cluster `label` of the factorised model, theta unchanged.
+
+        The reference refits every cluster from scratch in every sequential iteration
+        (REF/cGP/cGP_constrained.py:276,315-327).  When the old samples keep their labels only one cluster changes,
+        and at fixed theta its factor grows by one row: two triangular mat-vecs against the stored W = L^-1 (2 n^2
+        flops) instead of a Cholesky (n^3/3) — ``cgp_append_sample``.  The cluster's targets are re-normalised
+        (SK/_gpr.py:275-280) and alpha = K^-1 y, the LML value and the incumbent follow (``cgp_refresh_alpha``).
+        Result == a from-scratch ``set_theta(self.theta)`` on the extended data (tests/test_gpu_append.py, 1e-10).
+        Re-optimising theta afterwards is ``fit(R, theta0=self.theta)`` (run 0 of each cluster starts at its optimum)."""
+        if self.model is None:
+            raise _lib.CgpError("append() needs a factorised model (fit / set_theta first)")
+        c = int(label)
+        if not 0 <= c < self.C:
+            raise ValueError("label must be an existing cluster id (a new cluster needs a full refit)")
+        x = np.asarray(x, dtype=np.float64).reshape(1, self.d)
+        dev = self.device
+        m = self.model
+        old_offs, old_npad, old_moff = self.offs.copy(), self.npad.copy(), self.moff.copy()
+        pos = int(old_offs[c + 1])  # row of the new sample in cluster-sorted order (stable sort: last of its cluster)
+        self.X_host = np.concatenate([self.X_host, x])
+        self.y_host = np.append(self.y_host, float(y))
+        self.labels_host = np.append(self.labels_host, np.int64(c))
+        self.order = np.concatenate([self.order[:pos], [self.n], self.order[pos:]]).astype(self.order.dtype)
+        self.n += 1
+        self.counts = self.counts.copy()
+        self.counts[c] += 1
+        self.offs = np.concatenate([[0], np.cumsum(self.counts)]).astype(np.int64)
+        # targets of cluster c: new statistics, re-normalised (same code path as __init__)
+        seg = self.y_host[self.order[self.offs[c]:self.offs[c + 1]]]
+        self.y_max[c] = np.max(seg)
+        if self._normalize_y:
+            mu, sd = np.mean(seg), np.std(seg)
+            if sd < 10 * np.finfo(np.float64).eps:
+                sd = 1.0
+            self.y_mean[c], self.y_std[c] = mu, sd
+        yn = np.concatenate([self.yn_host[:pos], [0.0], self.yn_host[pos:]])
+        yn[self.offs[c]:self.offs[c + 1]] = (seg - self.y_mean[c]) / self.y_std[c]
+        self.yn_host = yn
+        self.Xs = torch.cat([self.Xs[:pos], torch.from_numpy(x).to(dev), self.Xs[pos:]]).contiguous()
+        self.yn = torch.from_numpy(yn).to(dev)
+        self.X_orig = torch.cat([self.X_orig, torch.from_numpy(x).to(dev)]).contiguous()
+        self.labels_dev = torch.from_numpy(self.labels_host).to(dev)
+        self.y_mean_dev = torch.from_numpy(self.y_mean).to(dev)
+        self.y_std_dev = torch.from_numpy(self.y_std).to(dev)
+        self.y_max_dev = torch.from_numpy(self.y_max).to(dev)
+        # factor buffers: in place unless the cluster crosses a 128-row padding boundary
+        self.npad = np.asarray([_lib.padded_n(int(v)) for v in self.counts], dtype=np.int64)
+        self.moff = np.concatenate([[0], np.cumsum(self.npad * self.npad)]).astype(np.int64)
+        if self.npad[c] != old_npad[c]:
+            for key in ("L", "W"):
+                old = m[key]
+                new = torch.zeros(int(self.moff[-1]), dtype=torch.float64, device=dev)
+                for cc in range(self.C):
+                    po, pn = int(old_npad[cc]), int(self.npad[cc])
+                    src = old[old_moff[cc]:old_moff[cc + 1]].view(po, po)
+                    dst = new[self.moff[cc]:self.moff[cc + 1]].view(pn, pn)
+                    dst[:po, :po].copy_(src)
+                    if pn > po:
+                        dst.diagonal()[po:].fill_(1.0)  # identity pad
+                m[key] = new
+        av = torch.empty(self.n, dtype=torch.float64, device=dev)
+        av[:pos] = m["alpha_vec"][:pos]
+        av[pos + 1:] = m["alpha_vec"][pos:]
+        m["alpha_vec"] = av
+        pn, nc = int(self.npad[c]), int(self.counts[c])
+        Lc = m["L"][self.moff[c]:self.moff[c + 1]].view(pn, pn)
+        Wc = m["W"][self.moff[c]:self.moff[c + 1]].view(pn, pn)
+        ws = self._workspace(_lib.append_workspace_bytes(nc))
+        Xc = self.Xs[self.offs[c]:self.offs[c + 1]]
+        info = _lib.append_sample(Xc, m["theta_dev"][c], self.alpha, self.kind, Lc, Wc, ws)
+        lml = _lib.refresh_alpha(Lc, Wc, nc, self.yn[self.offs[c]:self.offs[c + 1]], av[self.offs[c]:self.offs[c + 1]], ws)
+        if int(info.item()) != 0:
+            raise np.linalg.LinAlgError(
+                f"The kernel of cluster {c} is not returning a positive definite matrix after appending a sample "
+                f"({int(info.item())}-th leading minor). Try gradually increasing the 'alpha' parameter "
+                "of your GaussianProcessRegressor estimator.")
+        m["lml"][c] = lml[0]
+        m["lml_host"] = m["lml"].cpu().numpy()
+        return self
 
     # ------------------------------------------------------------------ accessors (host copies)
     def L_of(self, c):

@@ -120,6 +120,27 @@ int cgp_ei_argmax(cgp_handle* h, int kind, const double* X, const int64_t* offs_
                   int64_t* best_idx, int64_t* best_cluster, void* workspace,
                   size_t workspace_bytes, void* stream);
 
+/* Incremental refit.  The reference re-clusters and re-factorises everything after
+ * each new sample (REF/cGP/cGP_constrained.py:276,315-327).  When the labels of the old samples did not change, the
+ * factor of the one cluster that received the sample is extended by one row at unchanged theta:
+ *   L' = [[L,0],[l^T,dd]],  l = W k,  dd = sqrt(kappa - l.l),  W' = [[W,0],[-(l^T W)/dd, 1/dd]]     (2 n^2 flops).
+ *   Xc [n_new, d]     rows of the cluster, the new sample LAST
+ *   theta [P]         the cluster's hyper-parameters (device)
+ *   L, W [npad,npad]  the cluster's padded factor blocks, npad = cgp_padded_n(n_new); the leading (n_new-1)^2 block
+ *                     holds the old factor, the rest the identity pad.  Row n_new-1 is written.
+ *   info[1]           0, or n_new when the extended matrix is not positive definite. */
+size_t cgp_append_workspace_bytes(int64_t n_new);
+int cgp_append_sample(cgp_handle* h, int kind, const double* Xc, int64_t n_new, int d,
+                      const double* theta, double alpha, double* L, double* W, int64_t npad,
+                      int32_t* info, void* workspace, size_t workspace_bytes, void* stream);
+
+/* alpha = K^-1 y = W^T (W y) and the log-marginal likelihood value of one factorised cluster
+ * (SK/_gpr.py:363-367, 601-617) - needed after an append because y is re-normalised when a sample arrives.
+ * Workspace: cgp_append_workspace_bytes(n). */
+int cgp_refresh_alpha(cgp_handle* h, const double* L, const double* W, int64_t npad, int64_t n,
+                      const double* y, double* alpha_out, double* lml, void* workspace,
+                      size_t workspace_bytes, void* stream);
+
 /* Measurement helper (bench / tests only): C[M,N] = A[M,K] * B[N,K]^T through the same fp64
  * tensor-core (DMMA) tile mainloop every factorisation step uses.  M,N multiples of 128, K of 32. */
 int cgp_dgemm_nt(cgp_handle* h, const double* A, const double* B, double* C, int64_t M, int64_t N,
