@@ -41,6 +41,8 @@ SIGNATURES = {
                               _vp, _vp, _vp, _sz, _vp]),
     "cgp_ei_argmax": (C.c_int, [_vp, C.c_int, _vp, _pi64, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                 _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "cgp_ei_argmax_pruned": (C.c_int, [_vp, C.c_int, _vp, _pi64, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                       _i64, _i64, _vp, _vp, _vp, _vp, _sz, _vp]),
     "cgp_append_workspace_bytes": (_sz, [_i64]),
     "cgp_append_sample": (C.c_int, [_vp, C.c_int, _vp, _i64, C.c_int, _vp, _f64, _vp, _vp, _i64, _vp, _vp, _sz, _vp]),
     "cgp_refresh_alpha": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _sz, _vp]),
@@ -265,8 +267,9 @@ def predict(X, offs, theta, W, alpha_vec, y_mean, y_std, Q, qlabel, kind, want_s
 
 
 def ei_argmax(X, offs, theta, W, alpha_vec, y_mean, y_std, y_max, Q, qlabel, kind, idx_base=0, want_arrays=False,
-              workspace=None):
-    """-> (best [score f64, idx i64, cluster i64] as CUDA tensors, score/mean/std arrays or None)."""
+              workspace=None, prune=False):
+    """-> (best [score f64, idx i64, cluster i64] as CUDA tensors, score/mean/std arrays or None).
+    prune=True: exact bound-pruned scan (cgp_ei_argmax_pruned): same selection, no per-candidate arrays."""
     o, po = _host_i64(offs)
     d = X.shape[1]
     m = Q.shape[0]
@@ -281,6 +284,15 @@ def ei_argmax(X, offs, theta, W, alpha_vec, y_mean, y_std, y_max, Q, qlabel, kin
         std = torch.empty(m, dtype=torch.float64, device=dev)
     if workspace is None:
         workspace = torch.empty(score_workspace_bytes(o, d, m), dtype=torch.uint8, device=dev)
+    if prune:
+        if want_arrays:
+            raise CgpError("the pruned scan has no per-candidate outputs (pruned candidates are never scored exactly)")
+        _chk(lib().cgp_ei_argmax_pruned(handle(dev.index), KIND[kind], _ptr(X), po, len(o) - 1, d, _ptr(theta), _ptr(W),
+                                        _ptr(alpha_vec), _ptr(y_mean), _ptr(y_std), _ptr(y_max), _ptr(Q),
+                                        _ptr(qlabel, torch.int64), m, int(idx_base), _ptr(bs), _ptr(bi, torch.int64),
+                                        _ptr(bc, torch.int64), _ptr(workspace, torch.uint8), workspace.numel(),
+                                        _stream()), "cgp_ei_argmax_pruned")
+        return (bs, bi, bc), (None, None, None)
     _chk(lib().cgp_ei_argmax(handle(dev.index), KIND[kind], _ptr(X), po, len(o) - 1, d, _ptr(theta), _ptr(W),
                              _ptr(alpha_vec), _ptr(y_mean), _ptr(y_std), _ptr(y_max), _ptr(Q),
                              _ptr(qlabel, torch.int64), m, int(idx_base), _ptr(score), _ptr(mean), _ptr(std),

@@ -88,7 +88,9 @@ class CGPRegressor:
         return dict(labels=ql.cpu().numpy(), mean=mean.cpu().numpy(), std=std.cpu().numpy(), score=score.cpu().numpy(),
                     best_score=float(bs.item()), best_idx=int(bi.item()), best_cluster=int(bc.item()))
 
-    def select_next(self, candidates, sharded=False):
-        """-> (x_next [d], score, idx).  Multi-GPU aware (see cgp_b200/dist.py)."""
-        x, score, idx, _cl = self.engine_.select_next(candidates, self.n_neighbors, sharded=sharded)
+    def select_next(self, candidates, sharded=False, prune=False):
+        """-> (x_next [d], score, idx).  Multi-GPU aware (see cgp_b200/dist.py).  prune=True: exact bound-pruned scan,
+        same selection (candidates whose EI bound from the predictive mean cannot reach the running best skip the
+        variance contraction)."""
+        x, score, idx, _cl = self.engine_.select_next(candidates, self.n_neighbors, sharded=sharded, prune=prune)
         return x, score, idx

@@ -142,6 +142,7 @@ extern "C" int cgp_create(cgp_handle** out, int device) {
 #undef SET3
 #undef SET2
     CGP_CHECK(set_smem(k_predict_vnorm, GEMM_SMEM_BYTES));
+    CGP_CHECK(set_smem(k_predict_vnorm_sel, GEMM_SMEM_BYTES));
     {
         const char* e = getenv("CGP_TILE_MODE");  // "big" | "small" | unset = by launch size (results are bit-identical)
         h->tile_mode = (e && !strcmp(e, "big")) ? 1 : (e && !strcmp(e, "small")) ? 2 : 0;
@@ -739,7 +740,7 @@ struct ScoreLayout {
     int64_t mch;  // candidates per chunk (multiple of 128)
     int nblk, Tmax;
     int64_t npad_max;
-    size_t o_perm, o_qs, o_sorted, o_hist, o_blkoff, o_coff, o_blkv, o_blkp, o_kstar, o_vpart, o_mraw, total;
+    size_t o_perm, o_qs, o_sorted, o_hist, o_blkoff, o_coff, o_blkv, o_blkp, o_kstar, o_vpart, o_mraw, o_sel, o_cnt, o_lb, total;
 };
 
 static ScoreLayout score_layout(const int64_t* offs, int C, int d, int64_t m) {
@@ -771,6 +772,9 @@ static ScoreLayout score_layout(const int64_t* offs, int C, int d, int64_t m) {
     L.o_kstar = take((size_t)mch * L.npad_max * 8);
     L.o_vpart = take((size_t)L.Tmax * mch * 8);
     L.o_mraw = take((size_t)mch * 8);
+    L.o_sel = take((size_t)mch * 4);
+    L.o_cnt = take(8);
+    L.o_lb = take(8);
     L.total = off;
     return L;
 }
@@ -784,7 +788,7 @@ static int run_score(HandleImpl* h, int kind, const double* X, const int64_t* of
                      const double* W, const double* alpha_vec, const double* y_mean, const double* y_std,
                      const double* y_max, const double* Q, const int64_t* qlabel, int64_t m, int64_t idx_base,
                      double* score, double* mean, double* std_, double* best_score, int64_t* best_idx,
-                     int64_t* best_cluster, void* workspace, size_t ws_bytes, cudaStream_t s) {
+                     int64_t* best_cluster, void* workspace, size_t ws_bytes, cudaStream_t s, bool prune = false) {
     if (C > 4096) return -5;
     ScoreLayout L = score_layout(offs, C, d, m);
     if (L.total > ws_bytes) return -100;
@@ -800,6 +804,9 @@ static int run_score(HandleImpl* h, int kind, const double* X, const int64_t* of
     double* kstar = reinterpret_cast<double*>(ws + L.o_kstar);
     double* vpart = reinterpret_cast<double*>(ws + L.o_vpart);
     double* mraw = reinterpret_cast<double*>(ws + L.o_mraw);
+    int* sel = reinterpret_cast<int*>(ws + L.o_sel);
+    int* cnt = reinterpret_cast<int*>(ws + L.o_cnt);
+    double* lb = reinterpret_cast<double*>(ws + L.o_lb);
     const long long* ql = reinterpret_cast<const long long*>(qlabel);
 
     KL(h, CLS_BUCKET, s, k_bucket_hist<<<L.nblk, 256, (size_t)C * 4, s>>>(ql, m, C, L.nblk, hist));
@@ -812,6 +819,7 @@ static int run_score(HandleImpl* h, int kind, const double* X, const int64_t* of
 
     const int P = d + 1;
     long long woff = 0;
+    if (prune) KL(h, CLS_SCORE_FINISH, s, k_set_double<<<1, 1, 0, s>>>(lb, -INFINITY));
     for (int c = 0; c < C; ++c) {
         const int64_t n = offs[c + 1] - offs[c];
         const int64_t npad = pad_n(n);
@@ -826,6 +834,16 @@ static int run_score(HandleImpl* h, int kind, const double* X, const int64_t* of
             int rc = launch_cross(h, kind, Qs + p0 * d, rows, Xc, n, d, th, kstar, npad, rows_pad, npad, 0, 0.0, s);
             if (rc) return rc;
             KL(h, CLS_MEAN, s, k_mean<<<(unsigned)((rows + 7) / 8), 256, 0, s>>>(kstar, alpha_vec + offs[c], (int)n, (int)npad, rows, mraw));
+            if (prune) {  // mean-only bound -> survivors -> exact variance / score of the survivors -> tighter bound
+                KL(h, CLS_SCORE_FINISH, s, k_prune_select<<<1, 1024, 0, s>>>(mraw, rows, th, d, y_mean, y_std, y_max, c, (double)n, lb,
+                                                                              sel, cnt, sorted + p0));
+                KL(h, CLS_PREDICT_VNORM, s, k_predict_vnorm_sel<<<(unsigned)((rows_pad / CGP_TILE) * T), CGP_GEMM_THREADS, GEMM_SMEM_BYTES, s>>>(
+                    Wc, kstar, vpart, (int)npad, L.mch, sel, cnt));
+                KL(h, CLS_SCORE_FINISH, s, k_score_finish_sel<<<(unsigned)((rows + 255) / 256), 256, 0, s>>>(
+                    vpart, L.mch, T, mraw, sel, cnt, th, d, y_mean, y_std, y_max, c, (double)n, sorted + p0));
+                KL(h, CLS_SCORE_FINISH, s, k_lb_update<<<1, 1024, 0, s>>>(sorted + p0, rows, lb));
+                continue;
+            }
             KL(h, CLS_PREDICT_VNORM, s, k_predict_vnorm<<<(unsigned)((rows_pad / CGP_TILE) * T), CGP_GEMM_THREADS, GEMM_SMEM_BYTES, s>>>(
                 Wc, kstar, vpart, (int)npad, L.mch));
             KL(h, CLS_SCORE_FINISH, s, k_score_finish<<<(unsigned)((rows + 255) / 256), 256, 0, s>>>(
@@ -893,4 +911,32 @@ extern "C" int cgp_ei_argmax(cgp_handle* hh, int kind, const double* X, const in
     if (!workspace) return -23;
     return run_score(h, kind, X, offs, C, d, theta, W, alpha_vec, y_mean, y_std, y_max, Q, qlabel, m, idx_base, score, mean,
                      std_, best_score, best_idx, best_cluster, workspace, ws_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int cgp_ei_argmax_pruned(cgp_handle* hh, int kind, const double* X, const int64_t* offs, int C, int d,
+                                    const double* theta, const double* W, const double* alpha_vec, const double* y_mean,
+                                    const double* y_std, const double* y_max, const double* Q, const int64_t* qlabel,
+                                    int64_t m, int64_t idx_base, double* best_score, int64_t* best_idx,
+                                    int64_t* best_cluster, void* workspace, size_t ws_bytes, void* stream) {
+    HandleImpl* h = static_cast<HandleImpl*>(hh);
+    if (!h) return -1;
+    if (kind != 0 && kind != 1) return -2;
+    if (!X) return -3;
+    if (!offs || C <= 0) return -4;
+    if (d < 1 || d > CGP_MAX_D) return -6;
+    if (!theta) return -7;
+    if (!W) return -8;
+    if (!alpha_vec) return -9;
+    if (!y_mean) return -10;
+    if (!y_std) return -11;
+    if (!y_max) return -12;
+    if (m <= 0) return -15;
+    if (!Q) return -13;
+    if (!qlabel) return -14;
+    if (!best_score) return -17;
+    if (!best_idx) return -18;
+    if (!best_cluster) return -19;
+    if (!workspace) return -20;
+    return run_score(h, kind, X, offs, C, d, theta, W, alpha_vec, y_mean, y_std, y_max, Q, qlabel, m, idx_base, nullptr,
+                     nullptr, nullptr, best_score, best_idx, best_cluster, workspace, ws_bytes, (cudaStream_t)stream, true);
 }

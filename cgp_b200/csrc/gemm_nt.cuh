@@ -33,6 +33,20 @@ __device__ __forceinline__ void gemm_load_rows(double* sm, const double* __restr
     }
 }
 
+// Same, but tile row r is row ridx[r] of g (ridx in shared memory): the candidate tiles of the pruned EI scan are
+// gathered from the surviving rows of the cross-kernel block without compacting it.
+template <int ROWS>
+__device__ __forceinline__ void gemm_load_rows_gather(double* sm, const double* __restrict__ g, long long ld,
+                                                      const int* __restrict__ ridx, int k0, int tid) {
+    constexpr int CPR = CGP_BK / 2;
+#pragma unroll
+    for (int i = 0; i < ROWS * CPR / CGP_GEMM_THREADS; ++i) {
+        int idx = tid + i * CGP_GEMM_THREADS;
+        int row = idx / CPR, c = idx % CPR;
+        cp_async16(sm + row * CGP_BK + gemm_swz(row, c) * 2, g + (long long)ridx[row] * ld + k0 + c * 2);
+    }
+}
+
 // acc[mt][nt][e]: row = wm*(BM/2) + mt*8 + g, col = wn*(BN/4) + nt*8 + 2*t + e   (g = lane>>2, t = lane&3)
 template <int BM, int BN>
 struct GemmAccT {
@@ -50,10 +64,10 @@ __device__ __forceinline__ void gemm_zero(GemmAccT<BM, BN>& acc) {
 }
 
 // K must be a positive multiple of CGP_BK.  smem: GEMM_SMEM_BYTES_T(BM, BN), 16-byte aligned.
-template <int BM, int BN>
+template <int BM, int BN, bool GATHER_B = false>
 __device__ __forceinline__ void gemm_mainloop(GemmAccT<BM, BN>& acc, double* smem, const double* __restrict__ gA,
                                               long long lda, const double* __restrict__ gB,
-                                              long long ldb, int K) {
+                                              long long ldb, int K, const int* __restrict__ bidx = nullptr) {
     constexpr int MT = GemmAccT<BM, BN>::MT, NT = GemmAccT<BM, BN>::NT;
     constexpr int A_ELEMS = BM * CGP_BK, B_ELEMS = BN * CGP_BK;
     const int tid = threadIdx.x;
@@ -68,7 +82,10 @@ __device__ __forceinline__ void gemm_mainloop(GemmAccT<BM, BN>& acc, double* sme
     for (int s = 0; s < CGP_STAGES - 1; ++s) {
         if (s < nk) {
             gemm_load_rows<BM>(sA + s * A_ELEMS, gA, lda, s * CGP_BK, tid);
-            gemm_load_rows<BN>(sB + s * B_ELEMS, gB, ldb, s * CGP_BK, tid);
+            if (GATHER_B)
+                gemm_load_rows_gather<BN>(sB + s * B_ELEMS, gB, ldb, bidx, s * CGP_BK, tid);
+            else
+                gemm_load_rows<BN>(sB + s * B_ELEMS, gB, ldb, s * CGP_BK, tid);
         }
         cp_async_commit();
     }
@@ -80,7 +97,10 @@ __device__ __forceinline__ void gemm_mainloop(GemmAccT<BM, BN>& acc, double* sme
             if (nx < nk) {
                 int slot = nx % CGP_STAGES;
                 gemm_load_rows<BM>(sA + slot * A_ELEMS, gA, lda, nx * CGP_BK, tid);
-                gemm_load_rows<BN>(sB + slot * B_ELEMS, gB, ldb, nx * CGP_BK, tid);
+                if (GATHER_B)
+                    gemm_load_rows_gather<BN>(sB + slot * B_ELEMS, gB, ldb, bidx, nx * CGP_BK, tid);
+                else
+                    gemm_load_rows<BN>(sB + slot * B_ELEMS, gB, ldb, nx * CGP_BK, tid);
             }
             cp_async_commit();
         }
@@ -377,5 +397,31 @@ k_predict_vnorm(const double* __restrict__ W, const double* __restrict__ Kstar, 
     gemm_zero(acc);
     gemm_mainloop<CGP_TILE, CGP_TILE>(acc, gemm_smem, W + (long long)ib * CGP_TILE * npad, npad,
                                       Kstar + (long long)ct * CGP_TILE * npad, npad, (ib + 1) * CGP_TILE);
+    gemm_colsumsq(acc, gemm_smem, vpart + (long long)ib * cand_stride + (long long)ct * CGP_TILE);
+}
+
+// Pruned scan: the same contraction for the SURVIVING candidates of a chunk only.  sel[0..*count) lists their rows in
+// Kstar (ascending); candidate tile ct holds survivors ct*128..ct*128+127 (the tail of the last tile repeats row
+// sel[0]; its results are never read).  The grid is sized for the whole chunk, tiles past the survivor count exit:
+// no host synchronisation is needed to size the launch.  Every surviving candidate accumulates exactly the k sequence
+// of k_predict_vnorm, so its variance (and score) has the same bits as in the exhaustive scan.
+__global__ void __launch_bounds__(CGP_GEMM_THREADS, 1)
+k_predict_vnorm_sel(const double* __restrict__ W, const double* __restrict__ Kstar, double* __restrict__ vpart, int npad,
+                    long long cand_stride, const int* __restrict__ sel, const int* __restrict__ count) {
+    const int T = npad / CGP_TILE;
+    const int ct = blockIdx.x / T;
+    const int cnt = *count;
+    if (ct * CGP_TILE >= cnt) return;
+    const int ib = T - 1 - (blockIdx.x % T);
+    __shared__ int ridx[CGP_TILE];
+    if (threadIdx.x < CGP_TILE) {
+        const int q = ct * CGP_TILE + threadIdx.x;
+        ridx[threadIdx.x] = sel[q < cnt ? q : 0];
+    }
+    __syncthreads();
+    GemmAcc acc;
+    gemm_zero(acc);
+    gemm_mainloop<CGP_TILE, CGP_TILE, true>(acc, gemm_smem, W + (long long)ib * CGP_TILE * npad, npad, Kstar, npad,
+                                            (ib + 1) * CGP_TILE, ridx);
     gemm_colsumsq(acc, gemm_smem, vpart + (long long)ib * cand_stride + (long long)ct * CGP_TILE);
 }

@@ -140,6 +140,96 @@ k_score_finish(const double* __restrict__ vpart, long long vstride, int T, const
     }
 }
 
+// ---- exact bound-pruned scan --------------------------------------------------------------------------------
+// EI(mu, sigma) grows with sigma, and the posterior variance never exceeds the prior variance (1 + noise) y_std^2
+// (it is the prior minus a sum of squares, SK/_gpr.py:482-483).  So  ub = EI(mu, sigma_prior) / n_c  bounds the score
+// of a candidate from its predictive MEAN alone (n_c flops instead of n_c^2).  A candidate whose bound is below the
+// best exact score found so far (`lb`, device scalar) can neither win nor tie; it skips the variance contraction.
+// Survivors are scored exactly as in the exhaustive scan (same bits), so the selected sample is identical.
+// The bound is inflated by 1e-9 relative: the computed EI is monotone in sigma only up to rounding (the two terms of
+// REF/cGP/acquisition.py:26 cancel by a factor ~Z^2 in the lower tail, i.e. relative errors up to ~1e-13).
+// One block of 1024 threads per chunk: thread t owns rows [t*per, (t+1)*per) -> survivors are listed in ascending order.
+__global__ void __launch_bounds__(1024)
+k_prune_select(const double* __restrict__ mraw, long long rows, const double* __restrict__ th, int d,
+               const double* __restrict__ ymean, const double* __restrict__ ystd, const double* __restrict__ ymax,
+               int cluster, double n_c, const double* __restrict__ lb, int* __restrict__ sel, int* __restrict__ count,
+               double* __restrict__ score_chunk) {
+    __shared__ int part[1024];
+    const int per = (int)((rows + 1023) / 1024);
+    const long long s = (long long)threadIdx.x * per, e = min(rows, s + per);
+    const double ys = ystd[cluster], ym = ymean[cluster], yx = ymax[cluster];
+    const double sd_prior = sqrt((1.0 + exp(th[d])) * (ys * ys));
+    const double bound = *lb;
+    unsigned long long keep = 0ull;  // per <= 64 (chunks hold at most 65536 candidates)
+    int c = 0;
+    for (long long r = s; r < e; ++r) {
+        const double ub = ei_value(ys * mraw[r] + ym, sd_prior, yx) / n_c;
+        const bool k = !(ub * (1.0 + 1e-9) + 1e-300 < bound);
+        if (k) {
+            keep |= 1ull << (int)(r - s);
+            ++c;
+        } else {
+            score_chunk[r] = -INFINITY;
+        }
+    }
+    part[threadIdx.x] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int run = 0;
+        for (int t = 0; t < 1024; ++t) {
+            int v = part[t];
+            part[t] = run;
+            run += v;
+        }
+        *count = run;
+    }
+    __syncthreads();
+    int o = part[threadIdx.x];
+    for (long long r = s; r < e; ++r)
+        if (keep >> (int)(r - s) & 1ull) sel[o++] = (int)r;
+}
+
+// exact score of survivor q (row sel[q] of the chunk); same arithmetic as k_score_finish.  grid ceil(rows/256)
+__global__ void __launch_bounds__(256)
+k_score_finish_sel(const double* __restrict__ vpart, long long vstride, int T, const double* __restrict__ mraw,
+                   const int* __restrict__ sel, const int* __restrict__ count, const double* __restrict__ th, int d,
+                   const double* __restrict__ ymean, const double* __restrict__ ystd, const double* __restrict__ ymax,
+                   int cluster, double n_c, double* __restrict__ score_chunk) {
+    const int q = blockIdx.x * 256 + threadIdx.x;
+    if (q >= *count) return;
+    const int r = sel[q];
+    double vs = 0.0;
+    for (int ib = 0; ib < T; ++ib) vs += vpart[(long long)ib * vstride + q];
+    const double noise = exp(th[d]);
+    double var = (1.0 + noise) - vs;
+    if (var < 0.0) var = 0.0;
+    const double ys = ystd[cluster];
+    const double sd = sqrt(var * (ys * ys));
+    const double mu = ys * mraw[r] + ymean[cluster];
+    score_chunk[r] = ei_value(mu, sd, ymax[cluster]) / n_c;
+}
+
+// lb = max(lb, max over the chunk's exact scores).  One block of 1024.
+__global__ void __launch_bounds__(1024)
+k_lb_update(const double* __restrict__ score_chunk, long long rows, double* __restrict__ lb) {
+    __shared__ double sv[32];
+    double v = -INFINITY;
+    for (long long i = threadIdx.x; i < rows; i += 1024) {
+        const double s = score_chunk[i];
+        if (s > v) v = s;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if ((threadIdx.x & 31) == 0) sv[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 32; ++w) v = fmax(v, sv[w]);
+        if (v > *lb) *lb = v;
+    }
+}
+
+__global__ void k_set_double(double* p, double v) { *p = v; }
+
 // ---- arg-max over bucket order (cluster-major, candidate-index-minor): the FIRST maximum wins, which is
 // "lowest cluster id, then lowest candidate index" (REF/cGP/cGP_constrained.py:305,376-378).
 __device__ __forceinline__ void argmax_combine(double& v, long long& p, double ov, long long op) {

@@ -411,17 +411,18 @@ class ClusterGPEngine:
         return _lib.predict(self.Xs, self.offs, m["theta_dev"], m["W"], m["alpha_vec"], self.y_mean_dev, self.y_std_dev,
                             Qd, qlabel, self.kind, return_std, ws)
 
-    def ei_scan(self, Q, k=3, idx_base=0, want_arrays=False, qlabel=None):
-        """Dense EI scan of candidates Q -> ((score, idx, cluster) CUDA 1-elem tensors, arrays)."""
+    def ei_scan(self, Q, k=3, idx_base=0, want_arrays=False, qlabel=None, prune=False):
+        """Dense EI scan of candidates Q -> ((score, idx, cluster) CUDA 1-elem tensors, arrays).
+        prune=True: exact bound-pruned scan, identical selection (see cgp_ei_argmax_pruned)."""
         Qd = self._to_dev(Q)
         if qlabel is None:
             qlabel = self.route(Qd, k)
         m = self.model
         ws = self._workspace(_lib.score_workspace_bytes(self.offs, self.d, Qd.shape[0]))
         return _lib.ei_argmax(self.Xs, self.offs, m["theta_dev"], m["W"], m["alpha_vec"], self.y_mean_dev,
-                              self.y_std_dev, self.y_max_dev, Qd, qlabel, self.kind, idx_base, want_arrays, ws)
+                              self.y_std_dev, self.y_max_dev, Qd, qlabel, self.kind, idx_base, want_arrays, ws, prune)
 
-    def select_next(self, candidates, k=3, sharded=False):
+    def select_next(self, candidates, k=3, sharded=False, prune=False):
         """Pick the next sample from `candidates` [M,d].
 
         sharded=False: `candidates` is the full array (identical on every rank); each rank scores its
@@ -442,7 +443,7 @@ class ClusterGPEngine:
             lo, hi = cdist.shard_range(M, rank, ws)
             local = self._to_dev(candidates[lo:hi])
             base = lo
-        (bs, bi, bc), _ = self.ei_scan(local, k, idx_base=base)
+        (bs, bi, bc), _ = self.ei_scan(local, k, idx_base=base, prune=prune)
         li = int(bi.item()) - base
         x_local = local[li] if li >= 0 else torch.zeros(self.d, dtype=torch.float64, device=self.device)
         score, idx, cl, x, _owner = cdist.reduce_best(bs, bi, bc, x_local, rank, ws)

@@ -120,6 +120,17 @@ int cgp_ei_argmax(cgp_handle* h, int kind, const double* X, const int64_t* offs_
                   int64_t* best_idx, int64_t* best_cluster, void* workspace,
                   size_t workspace_bytes, void* stream);
 
+/* Same selection as cgp_ei_argmax (identical best_score bits, best_idx, best_cluster) with exact bound pruning:
+ * EI grows with sigma and the posterior variance never exceeds the prior one, so EI(mean_i, sigma_prior)/n_c bounds
+ * score_i from the predictive mean alone; candidates whose bound is below the best exact score found so far skip the
+ * n_c^2 variance contraction.  No per-candidate outputs (pruned candidates have no exact score). */
+int cgp_ei_argmax_pruned(cgp_handle* h, int kind, const double* X, const int64_t* offs_host,
+                         int n_clusters, int d, const double* theta, const double* W,
+                         const double* alpha_vec, const double* y_mean, const double* y_std,
+                         const double* y_max, const double* Q, const int64_t* qlabel, int64_t m,
+                         int64_t idx_base, double* best_score, int64_t* best_idx,
+                         int64_t* best_cluster, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Incremental refit.  The reference re-clusters and re-factorises everything after
  * each new sample (REF/cGP/cGP_constrained.py:276,315-327).  When the labels of the old samples did not change, the
  * factor of the one cluster that received the sample is extended by one row at unchanged theta:
