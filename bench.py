@@ -325,17 +325,22 @@ def run_b200(args, p):
             alg["trtri_trail"] += e_c * 2.0 * nt * TILE * ksum
         alg["lauum"] += e_c * n_c ** 3 / 3.0
     alg["predict_vnorm"] = args.steps * m_local * float(np.mean(sizes ** 2))
+    # k_lauum and k_predict_vnorm run alone on the caller's stream: their event brackets are exclusive kernel time.
+    # The trailing-update kernels of the Cholesky / triangular inverse run on three streams at once (chain, bulk,
+    # inverse: look-ahead schedule), so their brackets include the time they share the SMs with the other two streams;
+    # they are listed (overlapped=true) but the roofline kernel is taken from the exclusive ones.
+    exclusive = {"lauum", "predict_vnorm"}
     roof_all = {}
     for k, fl in alg.items():
         ms, cnt = prof[k]
         if ms > 0:
-            roof_all[k] = {"ms": ms, "launches": cnt, "achieved": fl / (ms * 1e-3) / 1e12, "share_of_step": ms * 1e-3 / t_dev}
-    fit_classes = ["assemble", "potrf_update", "potrf_trail", "potrf_diag", "potrf_panel", "trtri_acc", "trtri_trail",
-                   "trtri_scale", "solve_lml", "lauum", "grad"]
-    fit_ms = sum(prof[k][0] for k in fit_classes)
-    fit_unit = {"ms": fit_ms, "achieved": float(np.sum(ev_c * sizes ** 3)) / (fit_ms * 1e-3) / 1e12,
-                "note": "whole LML+gradient unit: n_c^3 algorithmic flops per evaluation over the summed kernel time of all fit kernels"}
-    top = max(roof_all, key=lambda k: roof_all[k]["ms"])
+            roof_all[k] = {"ms": ms, "launches": cnt, "achieved": fl / (ms * 1e-3) / 1e12, "share_of_step": ms * 1e-3 / t_dev,
+                           "overlapped": k not in exclusive}
+    fit_wall = res["fit_s"] * args.steps
+    fit_unit = {"s": fit_wall, "achieved": float(np.sum(ev_c * sizes ** 3)) / fit_wall / 1e12,
+                "note": "whole LML+gradient unit: n_c^3 algorithmic flops per evaluation (potrf + inverse + K^-1) over the "
+                        "fit wall time of the timed region, all kernels, host L-BFGS-B and final factorisation included"}
+    top = max((k for k in roof_all if k in exclusive), key=lambda k: roof_all[k]["ms"])
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
