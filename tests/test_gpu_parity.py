@@ -393,3 +393,38 @@ def test_workspace_hygiene_nan_fill_and_canaries(lib):
     (bs2, bi2, bc2), _ = lib.ei_argmax(Xd, offs, dev(th[:C]), m["W"], m["alpha_vec"], dev(np.zeros(C)), ones, dev(np.zeros(C)),
                                         dev(Q), ql, "matern32", 0, False)
     assert int(bi2.item()) == int(bi.item()) and float(bs2.item()) == float(bs.item())
+    # pruned scan with a poisoned workspace: same winner, canary intact
+    wsp = poisoned(need_s)
+    (bs3, bi3, bc3), _ = lib.ei_argmax(Xd, offs, dev(th[:C]), m["W"], m["alpha_vec"], dev(np.zeros(C)), ones, dev(np.zeros(C)),
+                                        dev(Q), ql, "matern32", 0, False, wsp[:need_s], True)
+    assert canary_ok(wsp, need_s)
+    assert int(bi3.item()) == int(bi.item()) and float(bs3.item()) == float(bs.item()) and int(bc3.item()) == int(bc.item())
+    # rank-1 append + alpha refresh on poisoned workspaces / poisoned new rows
+    c, n_old = 1, sizes[1]
+    n_new = n_old + 1
+    npad = lib.padded_n(n_new)
+    assert npad == lib.padded_n(n_old)
+    o = int(sum(lib.padded_n(v) ** 2 for v in sizes[:c]))
+    Lc = m["L"][o:o + npad * npad].view(npad, npad).clone()
+    Wc = m["W"][o:o + npad * npad].view(npad, npad).clone()
+    x_new = rng.uniform(size=(1, d))
+    Xc = dev(np.vstack([X[offs[c]:offs[c + 1]], x_new]))
+    need_a = lib.append_workspace_bytes(n_new)
+    wa = poisoned(need_a)
+    info = lib.append_sample(Xc, dev(th[c]), 1e-5, "matern32", Lc, Wc, wa[:need_a])
+    assert canary_ok(wa, need_a) and int(info.item()) == 0
+    Kn = oracle.kernel_matrix(np.vstack([X[offs[c]:offs[c + 1]], x_new]), th[c], "matern32", 1e-5)
+    Ln = np.linalg.cholesky(Kn)
+    assert np.max(np.abs(Lc[:n_new, :n_new].cpu().numpy() - Ln)) < 1e-11
+    assert np.max(np.abs(Wc[:n_new, :n_new].cpu().numpy() @ Ln - np.eye(n_new))) < 1e-9
+    assert float(Lc[n_new, n_new].item()) == 1.0 and float(Lc[n_new - 1, n_new].item()) == 0.0  # pad untouched
+    y_c = dev(rng.standard_normal(n_new))
+    a_out = torch.full((n_new + 8,), float("nan"), dtype=torch.float64, device="cuda")
+    wa2 = poisoned(need_a)
+    lml_c = lib.refresh_alpha(Lc, Wc, n_new, y_c, a_out[:n_new], wa2[:need_a])
+    assert canary_ok(wa2, need_a) and bool(torch.isnan(a_out[n_new:]).all())
+    a_ref = np.linalg.solve(Kn, y_c.cpu().numpy())
+    assert np.max(np.abs(a_out[:n_new].cpu().numpy() - a_ref)) <= 1e-9 * np.max(np.abs(a_ref))
+    z = np.linalg.solve(Ln, y_c.cpu().numpy())
+    lml_ref = -0.5 * z @ z - np.log(np.diag(Ln)).sum() - 0.5 * n_new * np.log(2 * np.pi)
+    assert abs(float(lml_c.item()) - lml_ref) <= 1e-10 * abs(lml_ref)

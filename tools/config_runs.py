@@ -1,5 +1,5 @@
 """Timings of the other BASELINE.json configs on ONE B200 (bench.py's headline is config 3).
-    python tools/config_runs.py cfg2 | cfg5 [--m M] | cfg4 [--n N --m M]
+    python tools/config_runs.py cfg1 | cfg2 | cfg5 [--m M] | cfg4 [--n N --m M]
 Data definitions: SURVEY.md §8d."""
 import json
 import os
@@ -82,6 +82,31 @@ def run_fit_scan(name, X, y, lab, Q, R, extra):
     print(json.dumps(out))
 
 
+def cfg1():
+    """configs[0] through the GPU-backend driver: `cGP.py -p 20 -s 10 -c 3 -n 3` on Bukin N6, seed 123
+    (the reference's own CPU run of this command takes 10.7 s of loop time in the build container)."""
+    import tempfile
+
+    from cgp_b200 import driver
+
+    with tempfile.TemporaryDirectory() as tmp:
+        cwd = os.getcwd()
+        os.chdir(tmp)
+        try:
+            driver.main(["-p", "20", "-s", "2", "-c", "3", "-n", "3", "-f", "cgp_b200.plugins.f_bukin", "-r", "123", "-X", "-o", "warm"])
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            X, Y = driver.main(["-p", "20", "-s", "10", "-c", "3", "-n", "3", "-f", "cgp_b200.plugins.f_bukin", "-r", "123", "-X",
+                                "-o", "run"])
+            torch.cuda.synchronize()
+            t = time.perf_counter() - t0
+        finally:
+            os.chdir(cwd)
+    print(json.dumps(dict(config="cfg1", command="driver -p 20 -s 10 -c 3 -n 3 -f f_bukin -r 123 (DGM3 clustering on the host, R = 10 d = 20, "
+                          "65536 candidates per step)", loop_s=t, s_per_iteration=t / 10, samples=int(X.shape[0]),
+                          best_y=float(Y.max()))))
+
+
 def cfg4():
     """single cluster, 4-D Matern-3/2: blocked DMMA Cholesky stress (one LML+grad evaluation, final factorisation, scan)."""
     n = arg("--n", 65536)
@@ -109,7 +134,9 @@ def cfg4():
 if __name__ == "__main__":
     _lib.handle()
     which = sys.argv[1]
-    if which == "cfg2":
+    if which == "cfg1":
+        cfg1()
+    elif which == "cfg2":
         run_fit_scan("cfg2", *cfg2())
     elif which == "cfg5":
         run_fit_scan("cfg5", *cfg5())
