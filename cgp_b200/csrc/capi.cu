@@ -148,6 +148,7 @@ extern "C" int cgp_create(cgp_handle** out, int device) {
         h->tile_mode = (e && !strcmp(e, "big")) ? 1 : (e && !strcmp(e, "small")) ? 2 : 0;
     }
     CGP_CHECK(set_smem(k_potrf_diag, DIAG_SMEM_BYTES));
+
     *out = h;
     return 0;
 }

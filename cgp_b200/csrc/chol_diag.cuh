@@ -17,6 +17,15 @@
 
 extern __shared__ __align__(16) double diag_smem[];
 
+#ifdef DIAG_TIMING  // development probe (tools/dev/diag_timing.cu): clock stamps of thread 0 at phase boundaries
+#define DIAG_STAMP(i)                                          \
+    do {                                                       \
+        if (threadIdx.x == 0 && blockIdx.x == 0) g_diag_t[i] = clock64(); \
+    } while (0)
+#else
+#define DIAG_STAMP(i)
+#endif
+
 // The three serial 32-wide routines below are written as template recursions instead of runtime loops so that
 // every index of the per-thread arrays is a compile-time constant: the arrays stay in registers and the
 // shared-memory operands (broadcast reads at static offsets) are hoisted out of the dependent FMA chains.
@@ -138,6 +147,7 @@ k_potrf_diag(double* __restrict__ Abuf, double* __restrict__ Ubuf, double* __res
     double* tile = Abuf + m.a_off + (long long)j * CGP_TILE * ld + (long long)j * CGP_TILE;
     __shared__ int fail;
     if (tid == 0) fail = 0;
+    DIAG_STAMP(0);
 #pragma unroll 8
     for (int idx = tid; idx < CGP_TILE * CGP_TILE; idx += 256) {  // 64 asynchronous 8-byte copies in flight per thread
         int r = idx >> 7, c = idx & 127;
@@ -146,6 +156,7 @@ k_potrf_diag(double* __restrict__ Abuf, double* __restrict__ Ubuf, double* __res
     cp_async_commit();
     cp_async_wait<0>();
     __syncthreads();
+    DIAG_STAMP(1);
 
     // ---------------- potrf, blocked by 32
 #pragma unroll 1
@@ -164,6 +175,7 @@ k_potrf_diag(double* __restrict__ Abuf, double* __restrict__ Ubuf, double* __res
             if (lane == 0 && failcol >= 0 && fail == 0) fail = k0 + failcol + 1;
         }
         __syncthreads();
+        DIAG_STAMP(2 + 3 * (k0 / 32));
         const int mrem = CGP_TILE - k0 - 32;
         if (tid < mrem) {  // sub-panel below the diagonal piece: one thread per row
             double* xr = S + (k0 + 32 + tid) * DIAG_LD + k0;
@@ -175,6 +187,7 @@ k_potrf_diag(double* __restrict__ Abuf, double* __restrict__ Ubuf, double* __res
             for (int c = 0; c < 32; ++c) xr[c] = x[c];
         }
         __syncthreads();
+        DIAG_STAMP(3 + 3 * (k0 / 32));
         if (mrem == 96)
             trail_update<6>(S, k0 + 32, k0, tid);
         else if (mrem == 64)
@@ -182,6 +195,7 @@ k_potrf_diag(double* __restrict__ Abuf, double* __restrict__ Ubuf, double* __res
         else if (mrem == 32)
             trail_update<2>(S, k0 + 32, k0, tid);
         __syncthreads();
+        DIAG_STAMP(4 + 3 * (k0 / 32));
     }
 
     // ---------------- write L_jj (strict upper zeroed), log-determinant partial, status
@@ -201,6 +215,7 @@ k_potrf_diag(double* __restrict__ Abuf, double* __restrict__ Ubuf, double* __res
         }
     }
     __syncthreads();
+    DIAG_STAMP(14);
 
     // ---------------- trtri (lower, in place), blocked by 32
     if (warp < 4) {  // the four diagonal pieces (their strict upper parts were zeroed above): lane = column
@@ -213,6 +228,7 @@ k_potrf_diag(double* __restrict__ Abuf, double* __restrict__ Ubuf, double* __res
             if (i >= lane) S[(k0 + i) * DIAG_LD + k0 + lane] = x[i];
     }
     __syncthreads();
+    DIAG_STAMP(15);
 #pragma unroll 1
     for (int b = 2; b >= 0; --b) {
         // phase 1: T[a,b] = sum_{a'=b+1}^{a} W[a,a'] L[a',b]   for a = b+1..3  (W trailing part already inverted)
@@ -289,6 +305,7 @@ k_potrf_diag(double* __restrict__ Abuf, double* __restrict__ Ubuf, double* __res
         D[r * CGP_TILE + c] = (c <= r) ? S[r * DIAG_LD + c] : 0.0;
         Ut[(long long)r * ld + c] = (c >= r) ? S[c * DIAG_LD + r] : 0.0;
     }
+    DIAG_STAMP(19);
 }
 
 // ---- y solves and the LML value ----------------------------------------------------------------
