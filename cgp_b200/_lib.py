@@ -46,6 +46,8 @@ SIGNATURES = {
     "cgp_append_workspace_bytes": (_sz, [_i64]),
     "cgp_append_sample": (C.c_int, [_vp, C.c_int, _vp, _i64, C.c_int, _vp, _f64, _vp, _vp, _i64, _vp, _vp, _sz, _vp]),
     "cgp_refresh_alpha": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "cgp_rowdot": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp]),
+    "cgp_argmax_sorted": (C.c_int, [_vp, _vp, _i64, _vp, _vp, C.c_int, _i64, _vp, _vp, _vp, _vp, _sz, _vp]),
     "cgp_dgemm_nt": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp]),
     "cgp_profile_classes": (C.c_int, []),
     "cgp_profile_class_name": (C.c_char_p, [C.c_int]),
@@ -231,6 +233,29 @@ def refresh_alpha(L_c, W_c, n, y_c, alpha_out, workspace):
                                  _ptr(alpha_out), _ptr(lml), _ptr(workspace, torch.uint8), workspace.numel(), _stream()),
          "cgp_refresh_alpha")
     return lml
+
+
+def rowdot(A, B, n):
+    """out[r] = sum_{k<n} A[r,k] B[r,k] for two contiguous [rows, ld] CUDA matrices."""
+    rows, ld = A.shape
+    assert B.shape == A.shape
+    out = torch.empty(rows, dtype=torch.float64, device=A.device)
+    _chk(lib().cgp_rowdot(handle(A.device.index), _ptr(A), _ptr(B), rows, int(n), ld, _ptr(out), _stream()), "cgp_rowdot")
+    return out
+
+
+def argmax_sorted(score_sorted, perm, coff, idx_base=0):
+    """First maximum in bucket order -> (score, candidate index + idx_base, cluster) 1-element CUDA tensors."""
+    dev = score_sorted.device
+    bs = torch.empty(1, dtype=torch.float64, device=dev)
+    bi = torch.empty(1, dtype=torch.int64, device=dev)
+    bc = torch.empty(1, dtype=torch.int64, device=dev)
+    scratch = torch.empty(16384, dtype=torch.uint8, device=dev)
+    _chk(lib().cgp_argmax_sorted(handle(dev.index), _ptr(score_sorted), score_sorted.numel(), _ptr(perm, torch.int64),
+                                 _ptr(coff, torch.int64), coff.numel() - 1, int(idx_base), _ptr(bs), _ptr(bi, torch.int64),
+                                 _ptr(bc, torch.int64), _ptr(scratch, torch.uint8), scratch.numel(), _stream()),
+         "cgp_argmax_sorted")
+    return bs, bi, bc
 
 
 def knn_labels(X, labels, Q, k, n_classes):

@@ -54,3 +54,9 @@ def mean_square_prediction_error(X, surrogate, X_sample, Y_sample, correct_label
     if VERBOSE:
         print("MSPE=", mspe, "\n")
     return mspe / X_sample.shape[0]
+
+
+def mean_square_prediction_error_batch(model, candidates):
+    """``mspe / n_c`` of a whole candidate array through the dense GPU scan (``model`` is a fitted CGPRegressor); equals
+    ``mean_square_prediction_error`` point by point for candidates routed to the cluster they are scored in."""
+    return model.mspe_candidates(candidates)

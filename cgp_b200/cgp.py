@@ -94,3 +94,18 @@ class CGPRegressor:
         variance contraction)."""
         x, score, idx, _cl = self.engine_.select_next(candidates, self.n_neighbors, sharded=sharded, prune=prune)
         return x, score, idx
+
+    def select_next_mspe(self, candidates):
+        """Dense scan of the reference's second acquisition (REF/cGP/acquisition.py:34-75, minimised):
+        -> (x_next [d], mspe / n_c, idx).  Single rank."""
+        eng = self.engine_
+        Q = eng._to_dev(candidates)
+        (v, i, _c), _ = eng.mspe_scan(Q, self.n_neighbors)
+        idx = int(i.item())
+        return Q[idx].cpu().numpy(), float(v.item()), idx
+
+    def mspe_candidates(self, candidates):
+        """mspe / n_c of every candidate (host array), the batched form of acquisition.mean_square_prediction_error."""
+        eng = self.engine_
+        _, arr = eng.mspe_scan(eng._to_dev(candidates), self.n_neighbors, want_arrays=True)
+        return arr.cpu().numpy()

@@ -941,3 +941,46 @@ extern "C" int cgp_ei_argmax_pruned(cgp_handle* hh, int kind, const double* X, c
     return run_score(h, kind, X, offs, C, d, theta, W, alpha_vec, y_mean, y_std, y_max, Q, qlabel, m, idx_base, nullptr,
                      nullptr, nullptr, best_score, best_idx, best_cluster, workspace, ws_bytes, (cudaStream_t)stream, true);
 }
+
+extern "C" int cgp_rowdot(cgp_handle* hh, const double* A, const double* B, int64_t rows, int64_t n, int64_t ld, double* out,
+                          void* stream) {
+    HandleImpl* h = static_cast<HandleImpl*>(hh);
+    if (!h) return -1;
+    if (!A) return -2;
+    if (!B) return -3;
+    if (rows < 0) return -4;
+    if (n < 0 || n > 0x7fffffff || ld < n) return -5;
+    if (!out) return -7;
+    if (rows == 0) return 0;
+    cudaStream_t s = (cudaStream_t)stream;
+    KL(h, CLS_SCORE_FINISH, s, k_rowdot<<<(unsigned)((rows + 7) / 8), 256, 0, s>>>(A, B, rows, (int)n, ld, out));
+    return (int)cudaGetLastError();
+}
+
+// First maximum of score_sorted[0..m) in bucket order (cluster-major, candidate-index-minor): the winner rule of
+// cgp_ei_argmax for scores the caller computed itself (dense MSPE scan).  perm[m] bucket position -> candidate index,
+// coff[C+1] bucket offsets (device).  scratch: 2 * 1024 * 8 bytes.
+extern "C" int cgp_argmax_sorted(cgp_handle* hh, const double* score_sorted, int64_t m, const int64_t* perm, const int64_t* coff,
+                                 int C, int64_t idx_base, double* best_score, int64_t* best_idx, int64_t* best_cluster,
+                                 void* scratch, size_t scratch_bytes, void* stream) {
+    HandleImpl* h = static_cast<HandleImpl*>(hh);
+    if (!h) return -1;
+    if (!score_sorted) return -2;
+    if (m <= 0) return -3;
+    if (!perm) return -4;
+    if (!coff || C <= 0) return -5;
+    if (!best_score) return -8;
+    if (!best_idx) return -9;
+    if (!best_cluster) return -10;
+    if (!scratch || scratch_bytes < 2 * 1024 * 8) return -11;
+    cudaStream_t s = (cudaStream_t)stream;
+    double* blkv = static_cast<double*>(scratch);
+    long long* blkp = reinterpret_cast<long long*>(static_cast<char*>(scratch) + 1024 * 8);
+    int nb = (int)std::min<long long>(1024, (m + 255) / 256);
+    KL(h, CLS_ARGMAX, s, k_argmax_blocks<<<nb, 256, 0, s>>>(score_sorted, m, blkv, blkp));
+    KL(h, CLS_ARGMAX, s, k_argmax_final<<<1, 256, 0, s>>>(blkv, blkp, nb, reinterpret_cast<const long long*>(perm),
+                                                          reinterpret_cast<const long long*>(coff), C, idx_base, best_score,
+                                                          reinterpret_cast<long long*>(best_idx),
+                                                          reinterpret_cast<long long*>(best_cluster)));
+    return (int)cudaGetLastError();
+}

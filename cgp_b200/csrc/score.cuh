@@ -303,3 +303,18 @@ k_argmax_final(const double* __restrict__ blkv, const long long* __restrict__ bl
         }
     }
 }
+
+// out[r] = sum_{k<n} A[r,k] * B[r,k]  (row-wise dot of two row-major [rows, ld] matrices).  warp per row, fixed order.
+// grid ceil(rows/8), block 256.  Used by the dense MSPE scan (quadratic form s_xo S_oo s_xo^T, REF/cGP/acquisition.py:68).
+__global__ void __launch_bounds__(256)
+k_rowdot(const double* __restrict__ A, const double* __restrict__ B, long long rows, int n, long long ld, double* __restrict__ out) {
+    const long long r = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (r >= rows) return;
+    const double* a = A + r * ld;
+    const double* b = B + r * ld;
+    double s = 0.0;
+    for (int k = lane; k < n; k += 32) s += a[k] * b[k];
+    s = warp_sum(s);
+    if (lane == 0) out[r] = s;
+}

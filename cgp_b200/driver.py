@@ -53,8 +53,8 @@ class cGP_constrained(object):
         if self.METHOD != "FREQUENTIST":
             raise NotImplementedError("only METHOD_CGP='FREQUENTIST' exists on the scikit-learn path of the reference "
                                       "(REF/cGP/cGP_constrained_module.py:423)")
-        if self.ACQUISITION != "EI":
-            raise NotImplementedError("ACQUISITION_CGP=MSPE has no dense-scan form yet; use cgp_b200.acquisition.mean_square_prediction_error pointwise")
+        if self.ACQUISITION not in ("EI", "MSPE"):
+            raise NotImplementedError("ACQUISITION_CGP must be 'EI' or 'MSPE' (REF/cGP/acquisition.py)")
 
     # ---- hooks (same names / meaning as the reference) ------------------------------------------------------------
     def f_Classify(self):
@@ -166,7 +166,15 @@ class cGP_constrained(object):
                 fitted_n, fitted_labels = n, labels.copy()
                 Q = self._candidates(bounds)
                 pen = self.boundary_penalty(Q, X)
-                if np.isscalar(pen) and pen == 0:
+                if self.ACQUISITION == "MSPE":  # minimised, REF/cGP/acquisition.py:69-75
+                    if np.isscalar(pen) and pen == 0:
+                        X_next, score, idx = model.select_next_mspe(Q)
+                    else:
+                        lab_q = model.predict_labels(Q)
+                        sc = model.mspe_candidates(Q) + np.asarray(pen, dtype=np.float64) / np.bincount(labels)[lab_q]
+                        idx = int(np.lexsort((np.arange(sc.shape[0]), lab_q, sc))[0])
+                        X_next, score = Q[idx], float(sc[idx])
+                elif np.isscalar(pen) and pen == 0:
                     X_next, score, idx = model.select_next(Q)
                 else:  # soft constraint: EI + penalty, then / n_c (REF/cGP/acquisition.py:29-32)
                     out = model.score_candidates(Q)
@@ -255,8 +263,8 @@ def main(argv=None):
         raise Exception("ERROR: N_SEQEUNTIAL(int) is a compulsory parameter that must be supplied. \n e.g. -s 20")
     if o.PILOT_FILE is None and o.N_PILOT is None:
         raise Exception("ERROR: Either N_PILOT(int) or PILOT_FILE(string, with extension) must be supplied.")
-    if o.ACQUISITION != "expected_improvement":
-        raise NotImplementedError("only -A expected_improvement runs on the GPU backend")
+    if o.ACQUISITION not in ("expected_improvement", "mean_square_prediction_error"):
+        raise NotImplementedError("-A must be expected_improvement or mean_square_prediction_error (REF/cGP/acquisition.py)")
     sys.path.insert(0, os.getcwd())
     ft = importlib.import_module(o.f_truth_py)  # -f: module with f_truth / get_bounds / censor_function / ... (:139-145)
     stamp = "".join(random.choice(string.ascii_lowercase) for _ in range(8))
@@ -294,7 +302,8 @@ def main(argv=None):
     run = Run({"N_PILOT_CGP": o.N_PILOT, "N_SEQUENTIAL_CGP": o.N_SEQUENTIAL, "RND_SEED_CGP": o.RND_SEED,
                "EXAMPLE_NAME_CGP": name, "EXPLORATION_RATE_CGP": o.EXPLORATION_RATE, "NO_CLUSTER_CGP": bool(o.NO_CLUSTER),
                "N_NEIGHBORS_CGP": o.N_NEIGHBORS, "N_COMPONENTS_CGP": o.N_COMPONENT, "N_CANDIDATES_CGP": o.CANDIDATES,
-               "N_RESTARTS_CGP": o.RESTARTS, "INCREMENTAL_CGP": o.INCREMENTAL, "PILOT_SAMPLES_CGP": o.PILOT_FILE, "OUTPUT_NAME_CGP": out,
+               "N_RESTARTS_CGP": o.RESTARTS, "INCREMENTAL_CGP": o.INCREMENTAL,
+               "ACQUISITION_CGP": "MSPE" if o.ACQUISITION == "mean_square_prediction_error" else "EI", "PILOT_SAMPLES_CGP": o.PILOT_FILE, "OUTPUT_NAME_CGP": out,
                "OBJ_NAME_CGP": o.OBJ_NAME, "VERBOSE_CGP": not o.QUIET})
     X, Y = run.run()
     if not o.QUIET:

@@ -376,6 +376,7 @@ class ClusterGPEngine:
                 "of your GaussianProcessRegressor estimator.")
         m["lml"][c] = lml[0]
         m["lml_host"] = m["lml"].cpu().numpy()
+        m.pop("_mspe", None)
         return self
 
     # ------------------------------------------------------------------ accessors (host copies)
@@ -421,6 +422,75 @@ class ClusterGPEngine:
         ws = self._workspace(_lib.score_workspace_bytes(self.offs, self.d, Qd.shape[0]))
         return _lib.ei_argmax(self.Xs, self.offs, m["theta_dev"], m["W"], m["alpha_vec"], self.y_mean_dev,
                               self.y_std_dev, self.y_max_dev, Qd, qlabel, self.kind, idx_base, want_arrays, ws, prune)
+
+    # ------------------------------------------------------------------ MSPE (the reference's second acquisition)
+    def _mspe_factors(self, c):
+        """Per-cluster matrices of the dense MSPE scan, padded [npad, npad], normalised-target units:
+        GT = I - Ko Kinv and Soo = Ko + noise I - Ko Kinv Ko, with Ko = Matern(X_c, X_c) (no White term: it is the
+        cross kernel K_trans of SK/_gpr.py:447) and Kinv = W^T W.  s_xo = k*^T G and S_oo are the blocks of the joint
+        posterior covariance `predict([x; X_sample], return_cov=True)` that REF/cGP/acquisition.py:52-57 slices."""
+        cache = self.model.setdefault("_mspe", {})
+        if c not in cache:
+            n, npad = int(self.counts[c]), int(self.npad[c])
+            th = self.model["theta_dev"][c].contiguous()
+            Xt = self.Xs[int(self.offs[c]):int(self.offs[c + 1])]
+            Ko = torch.zeros((npad, npad), dtype=torch.float64, device=self.device)
+            Ko[:n, :n] = _lib.kernel_cross(Xt, Xt, th, self.kind)
+            W = self.model["W"][int(self.moff[c]):int(self.moff[c + 1])].view(npad, npad)
+            Wt = W.t().contiguous()
+            Kinv = _lib.dgemm_nt(Wt, Wt)          # W^T W (pad block: identity)
+            KoKinv = _lib.dgemm_nt(Ko, Kinv)      # Ko Kinv (both symmetric)
+            GT = -KoKinv
+            GT.diagonal().add_(1.0)
+            Soo = Ko - _lib.dgemm_nt(KoKinv, Ko)
+            Soo.diagonal()[:n].add_(float(np.exp(self.theta[c][self.d])))
+            cache[c] = (GT, Soo)
+        return cache[c]
+
+    def mspe_scan(self, Q, k=3, idx_base=0, want_arrays=False, qlabel=None, chunk=16384):
+        """Dense scan of REF/cGP/acquisition.py:34-75 over candidates Q: for every candidate x routed to cluster c,
+        ``mspe = s_xx - s_xo S_oo s_xo^T`` from the joint posterior covariance of [x; X_c] (in the reference's units:
+        every covariance block carries y_std^2), value ``mspe / n_c``; the reference MINIMISES it, so the selected
+        candidate is the minimum, ties -> lowest cluster id, then lowest candidate index.
+        The two products are [m, n_c] x [n_c, n_c] GEMMs through the DMMA tile GEMM (cgp_dgemm_nt).
+        -> ((value, idx, cluster) 1-element CUDA tensors, value array in candidate order | None)."""
+        Qd = self._to_dev(Q)
+        M = Qd.shape[0]
+        if qlabel is None:
+            qlabel = self.route(Qd, k)
+        perm = torch.argsort(qlabel, stable=True)  # bucket order: cluster-major, candidate-index-minor
+        cnt = torch.bincount(qlabel, minlength=self.C)
+        coff = torch.zeros(self.C + 1, dtype=torch.int64, device=self.device)
+        coff[1:] = torch.cumsum(cnt, 0)
+        hoff = coff.cpu().numpy()
+        neg_sorted = torch.empty(M, dtype=torch.float64, device=self.device)
+        for c in range(self.C):
+            n, npad = int(self.counts[c]), int(self.npad[c])
+            if hoff[c + 1] == hoff[c]:
+                continue
+            GT, Soo = self._mspe_factors(c)
+            th = self.model["theta_dev"][c].contiguous()
+            Xt = self.Xs[int(self.offs[c]):int(self.offs[c + 1])]
+            ys = float(self.y_std[c])
+            for p0 in range(int(hoff[c]), int(hoff[c + 1]), chunk):
+                p1 = min(int(hoff[c + 1]), p0 + chunk)
+                m = p1 - p0
+                Qc = Qd[perm[p0:p1]].contiguous()
+                mpad = _lib.padded_n(m)
+                Ks = torch.zeros((mpad, npad), dtype=torch.float64, device=self.device)
+                Ks[:m, :n] = _lib.kernel_cross(Qc, Xt, th, self.kind)
+                Sxo = _lib.dgemm_nt(Ks, GT)      # s_xo = k*^T (I - Kinv Ko)
+                T2 = _lib.dgemm_nt(Sxo, Soo)     # s_xo S_oo
+                q = _lib.rowdot(T2, Sxo, n)[:m]
+                ql = torch.full((m,), c, dtype=torch.int64, device=self.device)
+                _, sd = self.predict(Qc, qlabel=ql, return_std=True)
+                neg_sorted[p0:p1] = -((sd * sd - (ys ** 6) * q) / float(n))
+        best = _lib.argmax_sorted(neg_sorted, perm, coff, idx_base)
+        arr = None
+        if want_arrays:
+            arr = torch.empty(M, dtype=torch.float64, device=self.device)
+            arr[perm] = -neg_sorted
+        return (-best[0], best[1], best[2]), arr
 
     def select_next(self, candidates, k=3, sharded=False, prune=False):
         """Pick the next sample from `candidates` [M,d].

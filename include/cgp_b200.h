@@ -152,6 +152,18 @@ int cgp_refresh_alpha(cgp_handle* h, const double* L, const double* W, int64_t n
                       const double* y, double* alpha_out, double* lml, void* workspace,
                       size_t workspace_bytes, void* stream);
 
+/* Building blocks of the dense MSPE scan (the reference's second acquisition, REF/cGP/acquisition.py:34-75: joint
+ * posterior covariance of [x; X_sample] from predict(return_cov=True), mspe = s_xx - s_xo S_oo s_xo^T).  As a scan over
+ * m candidates the two products are [m, n_c] x [n_c, n_c] GEMMs through cgp_dgemm_nt (cgp_b200/engine.py mspe_scan);
+ * cgp_rowdot finishes the quadratic form, cgp_argmax_sorted applies the winner rule of cgp_ei_argmax to scores in
+ * bucket order (cluster-major, candidate-index-minor).  scratch: 16 KiB. */
+int cgp_rowdot(cgp_handle* h, const double* A, const double* B, int64_t rows, int64_t n, int64_t ld,
+               double* out, void* stream);
+int cgp_argmax_sorted(cgp_handle* h, const double* score_sorted, int64_t m, const int64_t* perm,
+                      const int64_t* coff, int n_clusters, int64_t idx_base, double* best_score,
+                      int64_t* best_idx, int64_t* best_cluster, void* scratch, size_t scratch_bytes,
+                      void* stream);
+
 /* Measurement helper (bench / tests only): C[M,N] = A[M,K] * B[N,K]^T through the same fp64
  * tensor-core (DMMA) tile mainloop every factorisation step uses.  M,N multiples of 128, K of 32. */
 int cgp_dgemm_nt(cgp_handle* h, const double* A, const double* B, double* C, int64_t M, int64_t N,

@@ -40,7 +40,7 @@ def test_driver_rejects_unsupported():
     from cgp_b200.driver import cGP_constrained
 
     with pytest.raises(NotImplementedError):
-        cGP_constrained({"ACQUISITION_CGP": "MSPE"})
+        cGP_constrained({"ACQUISITION_CGP": "UCB"})
     with pytest.raises(NotImplementedError):
         cGP_constrained({"METHOD_CGP": "BAYESIAN"})
 
@@ -65,3 +65,24 @@ def test_driver_cli_end_to_end(tmp_path, monkeypatch):
     lab = obj["Classify"].predict(x)
     mu = [obj["GPR_list"][int(l)].predict(x[i:i + 1], return_std=True)[0][0] for i, l in enumerate(lab)]
     assert np.all(np.isfinite(mu))
+
+
+@pytest.mark.gpu
+def test_driver_mspe_acquisition():
+    """ACQUISITION_CGP='MSPE' (-A mean_square_prediction_error): the reference's second acquisition as a dense scan."""
+    from cgp_b200.driver import cGP_constrained
+    from cgp_b200.plugins import f_bukin
+
+    class Run(cGP_constrained):
+        def f_truth(self, X):
+            return f_bukin.f_truth(X)
+
+        def get_bounds(self, restrict):
+            return f_bukin.get_bounds(restrict)
+
+    r = Run({"N_PILOT_CGP": 18, "N_SEQUENTIAL_CGP": 2, "RND_SEED_CGP": 5, "NO_CLUSTER_CGP": True, "N_CANDIDATES_CGP": 1024,
+             "N_RESTARTS_CGP": 1, "ACQUISITION_CGP": "MSPE"})
+    X, Y = r.run()
+    assert X.shape == (20, 2) and all(h["mode"] == "acquisition" and np.isfinite(h["score"]) for h in r.history)
+    b = f_bukin.get_bounds(1)
+    assert np.all(X >= b[:, 0]) and np.all(X <= b[:, 1])

@@ -336,6 +336,55 @@ def test_return_cov_and_mspe_vs_reference():
         assert abs(got - want) <= 1e-7 * abs(want)
 
 
+def test_dense_mspe_scan_vs_reference_pointwise():
+    """The dense MSPE scan (engine.mspe_scan: two [m, n_c] x [n_c, n_c] DMMA GEMMs + row dot) against (a) the
+    reference's own outputs for a single cluster (tests/golden/cov_mspe_d3.npz, made by REF/cGP/acquisition.py:34-75)
+    and (b) the point-wise restatement with scikit-learn surrogates on a two-cluster model; selection = minimum,
+    ties to the lowest cluster id then index."""
+    from cgp_b200 import CGPRegressor
+    from cgp_b200.acquisition import mean_square_prediction_error, mean_square_prediction_error_batch
+    from sklearn.gaussian_process import GaussianProcessRegressor as SkGPR
+    from sklearn.gaussian_process.kernels import Matern, WhiteKernel
+    from sklearn.neighbors import KNeighborsClassifier as SkKNN
+
+    g = load_golden("cov_mspe_d3")
+    X, y, Q = g["X"], g["y"], g["Q"]
+    k = (Matern(length_scale=np.ones(3), length_scale_bounds=(1e-05, 100000.0), nu=3 / 2) +
+         WhiteKernel(noise_level=1.0, noise_level_bounds=(1e-05, 100000.0))).clone_with_theta(g["theta"])
+    m1 = CGPRegressor(kernel=k, alpha=1e-5, optimizer=None, random_state=0, n_neighbors=3).fit(X, y, np.zeros(len(y), dtype=int))
+    got = mean_square_prediction_error_batch(m1, Q)
+    k_g = len(g["mspe"])  # the golden file holds the reference's value for the first few candidates
+    assert got.shape == (Q.shape[0],) and np.max(np.abs(got[:k_g] - g["mspe"]) / np.abs(g["mspe"])) <= 1e-7
+    # two clusters, routed
+    rng = np.random.default_rng(9)
+    n, d, M = 420, 2, 3000
+    X = rng.uniform(size=(n, d))
+    lab = (X[:, 0] > 0.45).astype(np.int64)
+    y = lab + np.sin(5 * X.sum(1)) + 0.02 * rng.standard_normal(n)
+    Qs = rng.uniform(size=(M, d))
+    Qs[-100:] = Qs[:100]  # exact ties
+    th = np.array([[-0.8, -0.5, -4.0], [-0.3, -1.0, -3.0]])
+    from cgp_b200.engine import ClusterGPEngine
+
+    eng = ClusterGPEngine(X, y, lab, "matern32", 1e-5).set_theta(th)
+    (v, i, c), arr = eng.mspe_scan(Qs, 3, want_arrays=True)
+    arr = arr.cpu().numpy()
+    ql = eng.route(Qs, 3).cpu().numpy()
+    clf = SkKNN(n_neighbors=3).fit(X, lab)
+    assert np.array_equal(ql, clf.predict(Qs))
+    for cc in range(2):
+        kk = (Matern(length_scale=np.ones(d), length_scale_bounds=(1e-05, 100000.0), nu=3 / 2) +
+              WhiteKernel(noise_level=1.0, noise_level_bounds=(1e-05, 100000.0))).clone_with_theta(th[cc])
+        Xt, yt = X[lab == cc], y[lab == cc].reshape(-1, 1)
+        sk = SkGPR(kernel=kk, alpha=1e-5, normalize_y=True, optimizer=None, random_state=0).fit(Xt, yt)
+        for q in np.nonzero(ql == cc)[0][:25]:
+            want = mean_square_prediction_error(X=Qs[q], surrogate=sk, X_sample=Xt, Y_sample=yt, correct_label=np.float64(cc),
+                                                classify=clf, VERBOSE=False)
+            assert abs(arr[q] - want) <= 1e-6 * max(abs(want), 1e-12), (cc, q, arr[q], want)
+    order = np.lexsort((np.arange(M), ql, arr))  # minimum; ties -> lowest cluster id, then lowest index
+    assert int(i.item()) == int(order[0]) and int(c.item()) == int(ql[order[0]]) and float(v.item()) == arr[order[0]]
+
+
 def test_workspace_hygiene_nan_fill_and_canaries(lib):
     """compute-sanitizer is closed on this pool, so: (1) every workspace / output buffer is pre-filled with 0xFF bytes
     (NaN as fp64, -1 as int) — a kernel that consumed uninitialised memory would propagate NaN into the results;
