@@ -43,6 +43,8 @@ class cGP_constrained(object):
         # incremental refit: when the clustering keeps the labels of the old samples, append the
         # new sample to its cluster and re-optimise from the previous theta instead of refitting from scratch
         self.INCREMENTAL = g("INCREMENTAL_CGP", False)
+        # exact bound-pruned EI scan (cgp_ei_argmax_pruned): same selected sample, several times faster acquisition
+        self.PRUNED_SCAN = g("PRUNED_SCAN_CGP", False)
         self.PILOT_SAMPLES = g("PILOT_SAMPLES_CGP", None)
         self.OUTPUT_NAME = g("OUTPUT_NAME_CGP", None)
         self.OBJ_NAME = g("OBJ_NAME_CGP", None)
@@ -175,7 +177,7 @@ class cGP_constrained(object):
                         idx = int(np.lexsort((np.arange(sc.shape[0]), lab_q, sc))[0])
                         X_next, score = Q[idx], float(sc[idx])
                 elif np.isscalar(pen) and pen == 0:
-                    X_next, score, idx = model.select_next(Q)
+                    X_next, score, idx = model.select_next(Q, prune=bool(self.PRUNED_SCAN))
                 else:  # soft constraint: EI + penalty, then / n_c (REF/cGP/acquisition.py:29-32)
                     out = model.score_candidates(Q)
                     n_c = np.bincount(labels)[out["labels"]]
@@ -258,6 +260,7 @@ def main(argv=None):
     p.add_option("--candidates", type="int", dest="CANDIDATES", default=65536)
     p.add_option("--restarts", type="int", dest="RESTARTS", default=None)
     p.add_option("--incremental", action="store_true", dest="INCREMENTAL", default=False)
+    p.add_option("--pruned-scan", action="store_true", dest="PRUNED", default=False)
     o, _ = p.parse_args(argv)
     if o.N_SEQUENTIAL is None:
         raise Exception("ERROR: N_SEQEUNTIAL(int) is a compulsory parameter that must be supplied. \n e.g. -s 20")
@@ -302,7 +305,7 @@ def main(argv=None):
     run = Run({"N_PILOT_CGP": o.N_PILOT, "N_SEQUENTIAL_CGP": o.N_SEQUENTIAL, "RND_SEED_CGP": o.RND_SEED,
                "EXAMPLE_NAME_CGP": name, "EXPLORATION_RATE_CGP": o.EXPLORATION_RATE, "NO_CLUSTER_CGP": bool(o.NO_CLUSTER),
                "N_NEIGHBORS_CGP": o.N_NEIGHBORS, "N_COMPONENTS_CGP": o.N_COMPONENT, "N_CANDIDATES_CGP": o.CANDIDATES,
-               "N_RESTARTS_CGP": o.RESTARTS, "INCREMENTAL_CGP": o.INCREMENTAL,
+               "N_RESTARTS_CGP": o.RESTARTS, "INCREMENTAL_CGP": o.INCREMENTAL, "PRUNED_SCAN_CGP": o.PRUNED,
                "ACQUISITION_CGP": "MSPE" if o.ACQUISITION == "mean_square_prediction_error" else "EI", "PILOT_SAMPLES_CGP": o.PILOT_FILE, "OUTPUT_NAME_CGP": out,
                "OBJ_NAME_CGP": o.OBJ_NAME, "VERBOSE_CGP": not o.QUIET})
     X, Y = run.run()
