@@ -328,7 +328,8 @@ def ei_argmax(X, offs, theta, W, alpha_vec, y_mean, y_std, y_max, Q, qlabel, kin
 
 # ------------------------------------------------------------------------------------------------ measurement
 def profile_enable(on=True, device=None):
-    _chk(lib().cgp_profile_enable(handle(device), 1 if on else 0), "cgp_profile_enable")
+    """on: False/0 off, True/1 every launch timed, 2 only the large kernels (see include/cgp_b200.h)."""
+    _chk(lib().cgp_profile_enable(handle(device), int(on)), "cgp_profile_enable")
 
 
 def profile_read(reset=True, device=None):

@@ -43,7 +43,8 @@ struct HandleImpl : cgp_handle {
     cudaEvent_t ring_event;
     bool ring_event_pending;
     // per-kernel-class launch counters (always) and CUDA-event timing (when enabled)
-    bool prof_on;
+    int prof_on;      // 0 off, 1 every launch bracketed by events, 2 only the large kernels the roofline is quoted for
+    bool prof_skip;   // the launch in flight is counted but not timed
     std::vector<ProfRec> recs;
     size_t recs_used;
     double ms[CLS_COUNT];
@@ -58,6 +59,12 @@ struct HandleImpl : cgp_handle {
 static inline void prof_begin(HandleImpl* h, int cls, cudaStream_t s) {
     h->launches[cls]++;
     if (!h->prof_on) return;
+    // level 2: the event pair costs ~2 x 1.5 us of stream latency per launch, which is visible on the latency-bound
+    // chain of small kernels (diag / panel / update ...) when few matrices are in flight; time only the big ones.
+    h->prof_skip = h->prof_on == 2 && !(cls == CLS_LAUUM || cls == CLS_PREDICT_VNORM || cls == CLS_POTRF_TRAIL ||
+                                        cls == CLS_TRTRI_TRAIL || cls == CLS_KNN || cls == CLS_CROSS || cls == CLS_GRAD ||
+                                        cls == CLS_ASSEMBLE);
+    if (h->prof_skip) return;
     if (h->recs_used == h->recs.size()) {
         ProfRec r;
         cudaEventCreate(&r.a);
@@ -69,7 +76,7 @@ static inline void prof_begin(HandleImpl* h, int cls, cudaStream_t s) {
     cudaEventRecord(r.a, s);
 }
 static inline void prof_end(HandleImpl* h, cudaStream_t s) {
-    if (!h->prof_on) return;
+    if (!h->prof_on || h->prof_skip) return;
     cudaEventRecord(h->recs[h->recs_used].b, s);
     h->recs_used++;
 }
@@ -111,7 +118,8 @@ extern "C" int cgp_create(cgp_handle** out, int device) {
     h->pinned_used = 0;
     CGP_CHECK(cudaEventCreateWithFlags(&h->ring_event, cudaEventDisableTiming));
     h->ring_event_pending = false;
-    h->prof_on = false;
+    h->prof_on = 0;
+    h->prof_skip = false;
     h->recs_used = 0;
     {
         int lo = 0, hi = 0;
@@ -176,7 +184,7 @@ extern "C" int cgp_profile_classes(void) { return CLS_COUNT; }
 extern "C" const char* cgp_profile_class_name(int cls) { return (cls >= 0 && cls < CLS_COUNT) ? kClassNames[cls] : ""; }
 extern "C" int cgp_profile_enable(cgp_handle* hh, int on) {
     if (!hh) return -1;
-    static_cast<HandleImpl*>(hh)->prof_on = on != 0;
+    static_cast<HandleImpl*>(hh)->prof_on = on < 0 ? 0 : (on > 2 ? 2 : on);
     return 0;
 }
 // Folds the finished event pairs into ms[] (synchronises on them), copies the totals out and optionally resets.

@@ -169,9 +169,11 @@ int cgp_argmax_sorted(cgp_handle* h, const double* score_sorted, int64_t m, cons
 int cgp_dgemm_nt(cgp_handle* h, const double* A, const double* B, double* C, int64_t M, int64_t N,
                  int64_t K, void* stream);
 
-/* Measurement: every kernel launch is counted per kernel class; with profiling enabled each launch is also
- * bracketed by CUDA events on the caller's stream.  cgp_profile_read() folds the finished events into per-class
- * totals (milliseconds) and returns them with the launch counts (arrays of cgp_profile_classes() entries). */
+/* Measurement: every kernel launch is counted per kernel class; with profiling enabled launches are also bracketed by
+ * CUDA events on the stream they are launched on: on = 1 every launch, on = 2 only the large kernels (k_lauum,
+ * k_predict_vnorm, the trailing updates, k-NN, cross kernel, gradient, assembly) so that the event pairs do not sit on
+ * the latency-bound chain of small kernels.  cgp_profile_read() folds the finished events into per-class totals
+ * (milliseconds) and returns them with the launch counts (arrays of cgp_profile_classes() entries). */
 int cgp_profile_classes(void);
 const char* cgp_profile_class_name(int cls);
 int cgp_profile_enable(cgp_handle* h, int on);
