@@ -42,6 +42,31 @@ def test_binding_covers_header(built):
     assert _lib.lml_workspace_bytes([0, 5, 135], [0, 1, 1], 3) > 3 * 256 * 256 * 8
 
 
+def test_null_handle_is_rejected_without_touching_a_device(built):
+    """Every compute entry point returns -1 (argument 1 invalid, LAPACK style) for a NULL handle - checked here because
+    it needs no GPU; the full argument-error matrix runs on the GPU box (tests/test_gpu_parity.py)."""
+    import ctypes as C
+
+    from cgp_b200 import _lib
+
+    L = _lib.lib()
+    for name, (res, args) in _lib.SIGNATURES.items():
+        if res is not C.c_int or not args or args[0] is not C.c_void_p or name in ("cgp_destroy",):
+            continue
+        vals = []
+        for a in args:
+            if a in (C.c_void_p, _lib._pi64, _lib._pi32, C.POINTER(C.c_double)):
+                vals.append(None)  # NULL pointer
+            elif a is C.c_double:
+                vals.append(0.0)
+            else:
+                vals.append(0)
+        assert getattr(L, name)(*vals) == -1, name
+    assert L.cgp_destroy(None) == -1
+    assert L.cgp_append_workspace_bytes(0) == 0 and L.cgp_append_workspace_bytes(4100) > 3 * 4224 * 8
+    assert L.cgp_score_workspace_bytes(None, 0, 2, 10) == 0
+
+
 def test_no_cpu_fallback():
     """Without a CUDA device the product path must fail loudly, never compute on the CPU."""
     import numpy as np
