@@ -377,8 +377,11 @@ k_lauum(double* __restrict__ Abuf, const double* __restrict__ Ubuf, const MatMet
     if (i >= T) return;
     const long long ld = m.npad;
     const double* U = Ubuf + m.u_off;
+    // columns k >= n of U are the identity pad: zero in every real row, so whole k-chunks of pad are skipped (adds of
+    // exact zeros: same bits in the n x n part, which is all the gradient kernels read)
+    const int trim = (m.npad - m.n) / CGP_BK * CGP_BK;
     gemm_tile<0, BM, BN>(U + (long long)i * CGP_TILE * ld + (long long)i * CGP_TILE, ld,
-                         U + (long long)j * CGP_TILE * ld + (long long)i * CGP_TILE, ld, (T - i) * CGP_TILE,
+                         U + (long long)j * CGP_TILE * ld + (long long)i * CGP_TILE, ld, (T - i) * CGP_TILE - trim,
                          Abuf + m.a_off + (long long)i * CGP_TILE * ld + (long long)j * CGP_TILE, ld,
                          blockIdx.x % GEMM_PIECES(BM, BN));
 }
