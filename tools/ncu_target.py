@@ -1,5 +1,5 @@
 """Short single-GPU program for ncu: one batched LML+gradient evaluation (B pairs, n_c = 2048, d = 6), one final
-factorisation and one EI scan — every kernel of the hot path launches at least once.
+factorisation, one exhaustive and one pruned EI scan — every kernel of the hot path launches at least once.
     python tools/ncu_target.py [B] [n_c] [M]"""
 import os
 import sys
@@ -26,5 +26,7 @@ assert np.all(info == 0) and np.all(np.isfinite(lml))
 eng.set_theta(np.tile(np.array([-0.7] * d + [-4.0]), (Cn, 1)))
 Q = rng.uniform(size=(M, d))
 (bs, bi, bc), _ = eng.ei_scan(Q, 3)
+(ps, pi, pc), _ = eng.ei_scan(Q, 3, prune=True)  # exact bound-pruned scan: k_prune_select, k_predict_vnorm_sel, ...
 torch.cuda.synchronize()
+assert int(pi.item()) == int(bi.item()) and float(ps.item()) == float(bs.item())
 print("ok", float(lml[0]), int(bi.item()), float(bs.item()))
