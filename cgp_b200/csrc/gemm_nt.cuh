@@ -204,6 +204,26 @@ __device__ __forceinline__ void gemm_tile(const double* __restrict__ gA, long lo
     gemm_store<MODE, BM, BN>(acc, C + (long long)qi * BM * ldc + (long long)qj * BN, ldc);
 }
 
+// Rows >= n_c of the last tile row are the identity pad: L and A are zero there off the diagonal, so a Cholesky update
+// of those rows subtracts exact zeros.  When the lower 64 rows of tile row i are all pad (n_c <= 128 i + 64), only the
+// upper 64 rows of the tile are computed: the 128x128 CTA runs the 64x128 piece 0, the 64x64 pieces with qi = 1 exit.
+// Every computed element accumulates the same k sequence -> same bits.  (Config 3: six of eight clusters pad 4099..4173
+// rows to 4224, i.e. their 33rd tile row is 40-98 % pad; it takes part in 9 % of the trailing-update tiles.)
+template <int MODE, int BM, int BN>
+__device__ __forceinline__ void gemm_tile_rows(const MatMeta& m, int i, const double* __restrict__ gA, long long lda,
+                                               const double* __restrict__ gB, long long ldb, int K, double* __restrict__ C,
+                                               long long ldc, int piece) {
+    if (m.n <= i * CGP_TILE + 64) {
+        if (BM == CGP_TILE) {
+            static_assert(BM != CGP_TILE || BN == CGP_TILE, "the 128-row shape is 128x128");
+            gemm_tile<MODE, 64, CGP_TILE>(gA, lda, gB, ldb, K, C, ldc, 0);
+            return;
+        }
+        if (piece / (CGP_TILE / BN) == 1) return;
+    }
+    gemm_tile<MODE, BM, BN>(gA, lda, gB, ldb, K, C, ldc, piece);
+}
+
 // Plain C = A B^T (measurement + tests).  grid (N/128, M/128).
 __global__ void __launch_bounds__(CGP_GEMM_THREADS, 1)
 k_dgemm_nt(const double* __restrict__ A, const double* __restrict__ B, double* __restrict__ C, long long M,
@@ -231,9 +251,9 @@ k_potrf_update(double* __restrict__ Abuf, const MatMeta* __restrict__ meta, int 
     if (i >= T) return;
     double* A = Abuf + m.a_off;
     const long long ld = m.npad;
-    gemm_tile<2, BM, BN>(A + (long long)i * CGP_TILE * ld + (long long)kb * CGP_TILE, ld,
-                         A + (long long)j * CGP_TILE * ld + (long long)kb * CGP_TILE, ld, (j - kb) * CGP_TILE,
-                         A + (long long)i * CGP_TILE * ld + (long long)j * CGP_TILE, ld, blockIdx.x % GEMM_PIECES(BM, BN));
+    gemm_tile_rows<2, BM, BN>(m, i, A + (long long)i * CGP_TILE * ld + (long long)kb * CGP_TILE, ld,
+                              A + (long long)j * CGP_TILE * ld + (long long)kb * CGP_TILE, ld, (j - kb) * CGP_TILE,
+                              A + (long long)i * CGP_TILE * ld + (long long)j * CGP_TILE, ld, blockIdx.x % GEMM_PIECES(BM, BN));
 }
 
 // Trailing update after panel [c0, c1):  A[i,k] -= sum_{c=c0}^{c1-1} L[i,c] L[k,c]^T  for t0 <= k <= i < T  (t0 >= c1).
@@ -254,9 +274,9 @@ k_potrf_trail(double* __restrict__ Abuf, const MatMeta* __restrict__ meta, int c
     if (i >= T) return;
     double* A = Abuf + m.a_off;
     const long long ld = m.npad;
-    gemm_tile<2, BM, BN>(A + (long long)i * CGP_TILE * ld + (long long)c0 * CGP_TILE, ld,
-                         A + (long long)k * CGP_TILE * ld + (long long)c0 * CGP_TILE, ld, (c1 - c0) * CGP_TILE,
-                         A + (long long)i * CGP_TILE * ld + (long long)k * CGP_TILE, ld, blockIdx.x % GEMM_PIECES(BM, BN));
+    gemm_tile_rows<2, BM, BN>(m, i, A + (long long)i * CGP_TILE * ld + (long long)c0 * CGP_TILE, ld,
+                              A + (long long)k * CGP_TILE * ld + (long long)c0 * CGP_TILE, ld, (c1 - c0) * CGP_TILE,
+                              A + (long long)i * CGP_TILE * ld + (long long)k * CGP_TILE, ld, blockIdx.x % GEMM_PIECES(BM, BN));
 }
 
 // Same update restricted to the block columns k in [c1, c1 + H) (the next panel), rows i >= k.
@@ -272,9 +292,9 @@ k_potrf_head(double* __restrict__ Abuf, const MatMeta* __restrict__ meta, int c0
     if (i >= T) return;
     double* A = Abuf + m.a_off;
     const long long ld = m.npad;
-    gemm_tile<2, BM, BN>(A + (long long)i * CGP_TILE * ld + (long long)c0 * CGP_TILE, ld,
-                         A + (long long)k * CGP_TILE * ld + (long long)c0 * CGP_TILE, ld, (c1 - c0) * CGP_TILE,
-                         A + (long long)i * CGP_TILE * ld + (long long)k * CGP_TILE, ld, blockIdx.x % GEMM_PIECES(BM, BN));
+    gemm_tile_rows<2, BM, BN>(m, i, A + (long long)i * CGP_TILE * ld + (long long)c0 * CGP_TILE, ld,
+                              A + (long long)k * CGP_TILE * ld + (long long)c0 * CGP_TILE, ld, (c1 - c0) * CGP_TILE,
+                              A + (long long)i * CGP_TILE * ld + (long long)k * CGP_TILE, ld, blockIdx.x % GEMM_PIECES(BM, BN));
 }
 
 // Panel: L[i,j] = A[i,j] * inv(L[j,j])^T for i > j  (triangular solve recast as a GEMM with the explicitly inverted
