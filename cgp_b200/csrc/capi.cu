@@ -49,10 +49,12 @@ struct HandleImpl : cgp_handle {
     size_t recs_used;
     double ms[CLS_COUNT];
     long long launches[CLS_COUNT];
-    // second stream: the triangular-inverse chain of panel s runs beside the Cholesky chain of panel s+1
+    // internal streams of run_pipeline: sc (high priority) = the dependent chain update -> diag -> panel + look-ahead part
+    // of the trailing update; s2 (low priority) = triangular-inverse work of panel p beside the Cholesky of panel p+1.
+    // The caller's stream carries the bulk trailing updates and everything else; all three are joined before return.
     cudaStream_t s2, sc;
     int tile_mode;  // 0 = by launch size, 1 = always 128x128 CTAs, 2 = always the small shapes
-    std::vector<cudaEvent_t> panel_ev;
+    std::vector<cudaEvent_t> panel_ev;  // [2p] = panel p factored (on sc), [2p+1] = bulk update of panel p done (on s)
     cudaEvent_t join_ev, start_ev, chain_ev;
 };
 
