@@ -106,8 +106,10 @@ def _ptr(t, dtype=torch.float64):
     return t.data_ptr()
 
 
-def _stream():
-    return torch.cuda.current_stream().cuda_stream
+def _stream(device=None):
+    """Torch's current stream ON THE DEVICE OF THE TENSORS (not the process' current device): the C entry points run on
+    the handle's device whatever the caller's current device is."""
+    return torch.cuda.current_stream(device).cuda_stream
 
 
 def _host_i64(a):
@@ -134,7 +136,7 @@ def kernel_matrix(X, theta, kind="matern32", alpha=0.0):
     n, d = X.shape
     K = torch.empty((n, n), dtype=torch.float64, device=X.device)
     _chk(lib().cgp_kernel_matrix(handle(X.device.index), KIND[kind], _ptr(X), n, d, _ptr(theta), float(alpha), _ptr(K),
-                                 _stream()), "cgp_kernel_matrix")
+                                 _stream(X.device)), "cgp_kernel_matrix")
     return K
 
 
@@ -143,7 +145,7 @@ def kernel_cross(Q, X, theta, kind="matern32"):
     n = X.shape[0]
     K = torch.empty((m, n), dtype=torch.float64, device=X.device)
     _chk(lib().cgp_kernel_cross(handle(X.device.index), KIND[kind], _ptr(Q), m, _ptr(X), n, d, _ptr(theta), _ptr(K),
-                                _stream()), "cgp_kernel_cross")
+                                _stream(X.device)), "cgp_kernel_cross")
     return K
 
 
@@ -151,7 +153,7 @@ def dgemm_nt(A, B, out=None):
     M, K = A.shape
     N = B.shape[0]
     Cm = out if out is not None else torch.empty((M, N), dtype=torch.float64, device=A.device)
-    _chk(lib().cgp_dgemm_nt(handle(A.device.index), _ptr(A), _ptr(B), _ptr(Cm), M, N, K, _stream()), "cgp_dgemm_nt")
+    _chk(lib().cgp_dgemm_nt(handle(A.device.index), _ptr(A), _ptr(B), _ptr(Cm), M, N, K, _stream(A.device)), "cgp_dgemm_nt")
     return Cm
 
 
@@ -180,7 +182,7 @@ def lml_grad_batched(X, y, offs, pair_cluster, theta, alpha, kind, workspace, wa
         info = torch.empty(B, dtype=torch.int32, device=X.device)
     _chk(lib().cgp_lml_grad_batched(handle(X.device.index), KIND[kind], _ptr(X), _ptr(y), po, len(o) - 1, d, ppc, B,
                                     _ptr(theta), float(alpha), _ptr(lml), _ptr(grad), _ptr(info, torch.int32),
-                                    _ptr(workspace, torch.uint8), workspace.numel(), _stream()),
+                                    _ptr(workspace, torch.uint8), workspace.numel(), _stream(X.device)),
          "cgp_lml_grad_batched")
     return lml, grad, info
 
@@ -206,7 +208,7 @@ def factorize(X, y, offs, theta, alpha, kind, workspace=None):
         workspace = torch.empty(factorize_workspace_bytes(o, d), dtype=torch.uint8, device=dev)
     _chk(lib().cgp_factorize(handle(dev.index), KIND[kind], _ptr(X), _ptr(y), po, Cn, d, _ptr(theta), float(alpha),
                              _ptr(L), _ptr(W), _ptr(av), _ptr(lml), _ptr(info, torch.int32),
-                             _ptr(workspace, torch.uint8), workspace.numel(), _stream()), "cgp_factorize")
+                             _ptr(workspace, torch.uint8), workspace.numel(), _stream(dev)), "cgp_factorize")
     return dict(L=L, W=W, alpha_vec=av, lml=lml, info=info)
 
 
@@ -222,7 +224,7 @@ def append_sample(Xc, theta_c, alpha, kind, L_c, W_c, workspace):
     info = torch.empty(1, dtype=torch.int32, device=Xc.device)
     _chk(lib().cgp_append_sample(handle(Xc.device.index), KIND[kind], _ptr(Xc), n_new, d, _ptr(theta_c), float(alpha),
                                  _ptr(L_c), _ptr(W_c), npad, _ptr(info, torch.int32), _ptr(workspace, torch.uint8),
-                                 workspace.numel(), _stream()), "cgp_append_sample")
+                                 workspace.numel(), _stream(Xc.device)), "cgp_append_sample")
     return info
 
 
@@ -230,7 +232,7 @@ def refresh_alpha(L_c, W_c, n, y_c, alpha_out, workspace):
     """alpha_out[:n] = K^-1 y_c for one factorised cluster; -> lml (1-element CUDA tensor)."""
     lml = torch.empty(1, dtype=torch.float64, device=y_c.device)
     _chk(lib().cgp_refresh_alpha(handle(y_c.device.index), _ptr(L_c), _ptr(W_c), L_c.shape[0], int(n), _ptr(y_c),
-                                 _ptr(alpha_out), _ptr(lml), _ptr(workspace, torch.uint8), workspace.numel(), _stream()),
+                                 _ptr(alpha_out), _ptr(lml), _ptr(workspace, torch.uint8), workspace.numel(), _stream(y_c.device)),
          "cgp_refresh_alpha")
     return lml
 
@@ -240,7 +242,7 @@ def rowdot(A, B, n):
     rows, ld = A.shape
     assert B.shape == A.shape
     out = torch.empty(rows, dtype=torch.float64, device=A.device)
-    _chk(lib().cgp_rowdot(handle(A.device.index), _ptr(A), _ptr(B), rows, int(n), ld, _ptr(out), _stream()), "cgp_rowdot")
+    _chk(lib().cgp_rowdot(handle(A.device.index), _ptr(A), _ptr(B), rows, int(n), ld, _ptr(out), _stream(A.device)), "cgp_rowdot")
     return out
 
 
@@ -253,7 +255,7 @@ def argmax_sorted(score_sorted, perm, coff, idx_base=0):
     scratch = torch.empty(16384, dtype=torch.uint8, device=dev)
     _chk(lib().cgp_argmax_sorted(handle(dev.index), _ptr(score_sorted), score_sorted.numel(), _ptr(perm, torch.int64),
                                  _ptr(coff, torch.int64), coff.numel() - 1, int(idx_base), _ptr(bs), _ptr(bi, torch.int64),
-                                 _ptr(bc, torch.int64), _ptr(scratch, torch.uint8), scratch.numel(), _stream()),
+                                 _ptr(bc, torch.int64), _ptr(scratch, torch.uint8), scratch.numel(), _stream(dev)),
          "cgp_argmax_sorted")
     return bs, bi, bc
 
@@ -264,7 +266,7 @@ def knn_labels(X, labels, Q, k, n_classes):
     out = torch.empty(m, dtype=torch.int64, device=X.device)
     if m:
         _chk(lib().cgp_knn_labels(handle(X.device.index), _ptr(X), _ptr(labels, torch.int64), n, d, int(k),
-                                  int(n_classes), _ptr(Q), m, _ptr(out, torch.int64), _stream()), "cgp_knn_labels")
+                                  int(n_classes), _ptr(Q), m, _ptr(out, torch.int64), _stream(X.device)), "cgp_knn_labels")
     return out
 
 
@@ -286,7 +288,7 @@ def predict(X, offs, theta, W, alpha_vec, y_mean, y_std, Q, qlabel, kind, want_s
         workspace = torch.empty(score_workspace_bytes(o, d, m), dtype=torch.uint8, device=dev)
     _chk(lib().cgp_predict(handle(dev.index), KIND[kind], _ptr(X), po, len(o) - 1, d, _ptr(theta), _ptr(W),
                            _ptr(alpha_vec), _ptr(y_mean), _ptr(y_std), _ptr(Q), _ptr(qlabel, torch.int64), m,
-                           _ptr(mean), _ptr(std), _ptr(workspace, torch.uint8), workspace.numel(), _stream()),
+                           _ptr(mean), _ptr(std), _ptr(workspace, torch.uint8), workspace.numel(), _stream(dev)),
          "cgp_predict")
     return mean, std
 
@@ -316,13 +318,13 @@ def ei_argmax(X, offs, theta, W, alpha_vec, y_mean, y_std, y_max, Q, qlabel, kin
                                         _ptr(alpha_vec), _ptr(y_mean), _ptr(y_std), _ptr(y_max), _ptr(Q),
                                         _ptr(qlabel, torch.int64), m, int(idx_base), _ptr(bs), _ptr(bi, torch.int64),
                                         _ptr(bc, torch.int64), _ptr(workspace, torch.uint8), workspace.numel(),
-                                        _stream()), "cgp_ei_argmax_pruned")
+                                        _stream(dev)), "cgp_ei_argmax_pruned")
         return (bs, bi, bc), (None, None, None)
     _chk(lib().cgp_ei_argmax(handle(dev.index), KIND[kind], _ptr(X), po, len(o) - 1, d, _ptr(theta), _ptr(W),
                              _ptr(alpha_vec), _ptr(y_mean), _ptr(y_std), _ptr(y_max), _ptr(Q),
                              _ptr(qlabel, torch.int64), m, int(idx_base), _ptr(score), _ptr(mean), _ptr(std),
                              _ptr(bs), _ptr(bi, torch.int64), _ptr(bc, torch.int64), _ptr(workspace, torch.uint8),
-                             workspace.numel(), _stream()), "cgp_ei_argmax")
+                             workspace.numel(), _stream(dev)), "cgp_ei_argmax")
     return (bs, bi, bc), (score, mean, std)
 
 

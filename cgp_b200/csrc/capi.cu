@@ -90,6 +90,23 @@ static inline void prof_end(HandleImpl* h, cudaStream_t s) {
         prof_end(h, s);       \
     } while (0)
 
+// Every entry point that launches work runs on the handle's device, whatever the caller's current device is, and
+// restores the caller's device on return.
+struct DeviceGuard {
+    int prev = -1;
+    bool switched = false;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) switched = cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DeviceGuard() {
+        if (switched) cudaSetDevice(prev);
+    }
+};
+#define CGP_ENTER(hh)                                  \
+    HandleImpl* h = static_cast<HandleImpl*>(hh);      \
+    if (!h) return -1;                                 \
+    DeviceGuard guard_(h->device)
+
 template <typename K>
 static cudaError_t set_smem(K kernel, int bytes) {
     return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
@@ -106,23 +123,28 @@ extern "C" int64_t cgp_model_elems(const int64_t* offs, int C) {
     return s;
 }
 
-extern "C" int cgp_create(cgp_handle** out, int device) {
-    if (!out) return -1;
-    int cur = 0;
-    CGP_CHECK(cudaGetDevice(&cur));
-    if (cur != device) CGP_CHECK(cudaSetDevice(device));
-    HandleImpl* h = new (std::nothrow) HandleImpl();
-    if (!h) return (int)cudaErrorMemoryAllocation;
+// Releases whatever a (possibly partially constructed) handle owns.
+static void handle_free(HandleImpl* h) {
+    for (auto& r : h->recs) {
+        cudaEventDestroy(r.a);
+        cudaEventDestroy(r.b);
+    }
+    for (auto& e : h->panel_ev) cudaEventDestroy(e);
+    for (cudaEvent_t e : {h->join_ev, h->start_ev, h->chain_ev, h->ring_event})
+        if (e) cudaEventDestroy(e);
+    if (h->s2) cudaStreamDestroy(h->s2);
+    if (h->sc) cudaStreamDestroy(h->sc);
+    if (h->pinned) cudaFreeHost(h->pinned);
+    delete h;
+}
+
+static int handle_init(HandleImpl* h, int device) {
     h->device = device;
     CGP_CHECK(cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device));
     CGP_CHECK(cudaMallocHost(&h->pinned, PINNED_BYTES));
     h->pinned_bytes = PINNED_BYTES;
     h->pinned_used = 0;
     CGP_CHECK(cudaEventCreateWithFlags(&h->ring_event, cudaEventDisableTiming));
-    h->ring_event_pending = false;
-    h->prof_on = 0;
-    h->prof_skip = false;
-    h->recs_used = 0;
     {
         int lo = 0, hi = 0;
         CGP_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
@@ -133,7 +155,6 @@ extern "C" int cgp_create(cgp_handle** out, int device) {
         CGP_CHECK(cudaEventCreateWithFlags(&h->start_ev, cudaEventDisableTiming));
         CGP_CHECK(cudaEventCreateWithFlags(&h->chain_ev, cudaEventDisableTiming));
     }
-    for (int i = 0; i < CLS_COUNT; ++i) h->ms[i] = 0.0, h->launches[i] = 0;
     CGP_CHECK(set_smem(k_dgemm_nt, GEMM_SMEM_BYTES));
 #define SET3(K)                                                                       \
     CGP_CHECK(set_smem(K<128, 128>, GEMM_SMEM_BYTES_T(128, 128)));                    \
@@ -158,7 +179,31 @@ extern "C" int cgp_create(cgp_handle** out, int device) {
         h->tile_mode = (e && !strcmp(e, "big")) ? 1 : (e && !strcmp(e, "small")) ? 2 : 0;
     }
     CGP_CHECK(set_smem(k_potrf_diag, DIAG_SMEM_BYTES));
+    return 0;
+}
 
+extern "C" int cgp_create(cgp_handle** out, int device) {
+    if (!out) return -1;
+    *out = nullptr;
+    DeviceGuard guard(device);  // the caller's current device is restored on return
+    int cur = -1;
+    CGP_CHECK(cudaGetDevice(&cur));
+    if (cur != device) return (int)cudaErrorInvalidDevice;
+    HandleImpl* h = new (std::nothrow) HandleImpl();
+    if (!h) return (int)cudaErrorMemoryAllocation;
+    h->pinned = nullptr;
+    h->ring_event = h->join_ev = h->start_ev = h->chain_ev = nullptr;
+    h->s2 = h->sc = nullptr;
+    h->ring_event_pending = false;
+    h->prof_on = 0;
+    h->prof_skip = false;
+    h->recs_used = 0;
+    for (int i = 0; i < CLS_COUNT; ++i) h->ms[i] = 0.0, h->launches[i] = 0;
+    int rc = handle_init(h, device);
+    if (rc) {  // nothing leaks when a step of the construction fails
+        handle_free(h);
+        return rc;
+    }
     *out = h;
     return 0;
 }
@@ -166,19 +211,8 @@ extern "C" int cgp_create(cgp_handle** out, int device) {
 extern "C" int cgp_destroy(cgp_handle* hh) {
     if (!hh) return -1;
     HandleImpl* h = static_cast<HandleImpl*>(hh);
-    for (auto& r : h->recs) {
-        cudaEventDestroy(r.a);
-        cudaEventDestroy(r.b);
-    }
-    for (auto& e : h->panel_ev) cudaEventDestroy(e);
-    cudaEventDestroy(h->join_ev);
-    cudaEventDestroy(h->start_ev);
-    cudaEventDestroy(h->chain_ev);
-    cudaStreamDestroy(h->s2);
-    cudaStreamDestroy(h->sc);
-    cudaEventDestroy(h->ring_event);
-    cudaFreeHost(h->pinned);
-    delete h;
+    DeviceGuard guard(h->device);
+    handle_free(h);
     return 0;
 }
 
@@ -191,8 +225,7 @@ extern "C" int cgp_profile_enable(cgp_handle* hh, int on) {
 }
 // Folds the finished event pairs into ms[] (synchronises on them), copies the totals out and optionally resets.
 extern "C" int cgp_profile_read(cgp_handle* hh, double* ms, int64_t* launches, int n_cls, int reset) {
-    HandleImpl* h = static_cast<HandleImpl*>(hh);
-    if (!h) return -1;
+    CGP_ENTER(hh);
     for (size_t i = 0; i < h->recs_used; ++i) {
         float t = 0.f;
         CGP_CHECK(cudaEventSynchronize(h->recs[i].b));
@@ -247,8 +280,7 @@ static int launch_cross(HandleImpl* h, int kind, const double* Q, int64_t m, con
 
 extern "C" int cgp_kernel_matrix(cgp_handle* hh, int kind, const double* X, int64_t n, int d, const double* theta,
                                  double alpha, double* K, void* stream) {
-    HandleImpl* h = static_cast<HandleImpl*>(hh);
-    if (!h) return -1;
+    CGP_ENTER(hh);
     if (kind != 0 && kind != 1) return -2;
     if (!X || n < 0) return -3;
     if (d < 1 || d > CGP_MAX_D) return -5;
@@ -259,8 +291,7 @@ extern "C" int cgp_kernel_matrix(cgp_handle* hh, int kind, const double* X, int6
 
 extern "C" int cgp_kernel_cross(cgp_handle* hh, int kind, const double* Q, int64_t m, const double* X, int64_t n, int d,
                                 const double* theta, double* Kqx, void* stream) {
-    HandleImpl* h = static_cast<HandleImpl*>(hh);
-    if (!h) return -1;
+    CGP_ENTER(hh);
     if (kind != 0 && kind != 1) return -2;
     if (!Q || m < 0) return -3;
     if (!X || n < 0) return -5;
@@ -272,8 +303,7 @@ extern "C" int cgp_kernel_cross(cgp_handle* hh, int kind, const double* Q, int64
 
 extern "C" int cgp_dgemm_nt(cgp_handle* hh, const double* A, const double* B, double* C, int64_t M, int64_t N, int64_t K,
                             void* stream) {
-    HandleImpl* h = static_cast<HandleImpl*>(hh);
-    if (!h) return -1;
+    CGP_ENTER(hh);
     if (!A || !B || !C) return -2;
     if (M <= 0 || M % CGP_TILE || N <= 0 || N % CGP_TILE || K <= 0 || K % CGP_BK) return -5;
     dim3 grid((unsigned)(N / CGP_TILE), (unsigned)(M / CGP_TILE));
@@ -470,8 +500,7 @@ extern "C" int cgp_lml_grad_batched(cgp_handle* hh, int kind, const double* X, c
                                     int C, int d, const int32_t* pair_cluster, int B, const double* theta, double alpha,
                                     double* lml, double* grad, int32_t* info, void* workspace, size_t ws_bytes,
                                     void* stream) {
-    HandleImpl* h = static_cast<HandleImpl*>(hh);
-    if (!h) return -1;
+    CGP_ENTER(hh);
     if (kind != 0 && kind != 1) return -2;
     if (!X) return -3;
     if (!y) return -4;
@@ -566,8 +595,7 @@ extern "C" size_t cgp_factorize_workspace_bytes(const int64_t* offs, int C, int 
 extern "C" int cgp_factorize(cgp_handle* hh, int kind, const double* X, const double* y, const int64_t* offs, int C, int d,
                              const double* theta, double alpha, double* L, double* W, double* alpha_vec, double* lml,
                              int32_t* info, void* workspace, size_t ws_bytes, void* stream) {
-    HandleImpl* h = static_cast<HandleImpl*>(hh);
-    if (!h) return -1;
+    CGP_ENTER(hh);
     if (kind != 0 && kind != 1) return -2;
     if (!X) return -3;
     if (!y) return -4;
@@ -644,8 +672,7 @@ static void launch_tmatvec(HandleImpl* h, const double* W, int64_t ld, int n, co
 extern "C" int cgp_append_sample(cgp_handle* hh, int kind, const double* Xc, int64_t n_new, int d, const double* theta,
                                  double alpha, double* L, double* W, int64_t npad, int32_t* info, void* workspace,
                                  size_t ws_bytes, void* stream) {
-    HandleImpl* h = static_cast<HandleImpl*>(hh);
-    if (!h) return -1;
+    CGP_ENTER(hh);
     if (kind != 0 && kind != 1) return -2;
     if (!Xc) return -3;
     if (n_new < 1 || n_new > 0x7fffffff) return -4;
@@ -679,8 +706,7 @@ extern "C" int cgp_append_sample(cgp_handle* hh, int kind, const double* Xc, int
 
 extern "C" int cgp_refresh_alpha(cgp_handle* hh, const double* L, const double* W, int64_t npad, int64_t n, const double* y,
                                  double* alpha_out, double* lml, void* workspace, size_t ws_bytes, void* stream) {
-    HandleImpl* h = static_cast<HandleImpl*>(hh);
-    if (!h) return -1;
+    CGP_ENTER(hh);
     if (!L) return -2;
     if (!W) return -3;
     if (n < 1 || n > 0x7fffffff || npad != pad_n(n)) return -5;
@@ -718,8 +744,7 @@ static int launch_knn(HandleImpl* h, const double* X, const long long* lab, int 
 
 extern "C" int cgp_knn_labels(cgp_handle* hh, const double* X, const int64_t* labels, int64_t n, int d, int k, int n_classes,
                               const double* Q, int64_t m, int64_t* out, void* stream) {
-    HandleImpl* h = static_cast<HandleImpl*>(hh);
-    if (!h) return -1;
+    CGP_ENTER(hh);
     if (!X) return -2;
     if (!labels) return -3;
     if (n <= 0 || n > 0x7fffffff) return -4;
@@ -855,10 +880,13 @@ static int run_score(HandleImpl* h, int kind, const double* X, const int64_t* of
                 KL(h, CLS_SCORE_FINISH, s, k_lb_update<<<1, 1024, 0, s>>>(sorted + p0, rows, lb));
                 continue;
             }
-            KL(h, CLS_PREDICT_VNORM, s, k_predict_vnorm<<<(unsigned)((rows_pad / CGP_TILE) * T), CGP_GEMM_THREADS, GEMM_SMEM_BYTES, s>>>(
-                Wc, kstar, vpart, (int)npad, L.mch));
+            // mean-only callers (predict(return_std=False)) skip the n_c^2-per-candidate variance contraction
+            const bool need_var = std_ != nullptr || y_max != nullptr;
+            if (need_var)
+                KL(h, CLS_PREDICT_VNORM, s, k_predict_vnorm<<<(unsigned)((rows_pad / CGP_TILE) * T), CGP_GEMM_THREADS, GEMM_SMEM_BYTES, s>>>(
+                    Wc, kstar, vpart, (int)npad, L.mch));
             KL(h, CLS_SCORE_FINISH, s, k_score_finish<<<(unsigned)((rows + 255) / 256), 256, 0, s>>>(
-                vpart, L.mch, T, mraw, rows, p0, perm, th, d, y_mean, y_std, y_max, c, (double)n, mean, std_, score, sorted));
+                vpart, L.mch, need_var ? T : 0, mraw, rows, p0, perm, th, d, y_mean, y_std, y_max, c, (double)n, mean, std_, score, sorted));
         }
     }
     if (y_max && best_score && best_idx && best_cluster) {
@@ -875,8 +903,7 @@ extern "C" int cgp_predict(cgp_handle* hh, int kind, const double* X, const int6
                            const double* W, const double* alpha_vec, const double* y_mean, const double* y_std,
                            const double* Q, const int64_t* qlabel, int64_t m, double* mean, double* std_, void* workspace,
                            size_t ws_bytes, void* stream) {
-    HandleImpl* h = static_cast<HandleImpl*>(hh);
-    if (!h) return -1;
+    CGP_ENTER(hh);
     if (kind != 0 && kind != 1) return -2;
     if (!X) return -3;
     if (!offs || C <= 0) return -4;
@@ -901,8 +928,7 @@ extern "C" int cgp_ei_argmax(cgp_handle* hh, int kind, const double* X, const in
                              const double* y_std, const double* y_max, const double* Q, const int64_t* qlabel, int64_t m,
                              int64_t idx_base, double* score, double* mean, double* std_, double* best_score,
                              int64_t* best_idx, int64_t* best_cluster, void* workspace, size_t ws_bytes, void* stream) {
-    HandleImpl* h = static_cast<HandleImpl*>(hh);
-    if (!h) return -1;
+    CGP_ENTER(hh);
     if (kind != 0 && kind != 1) return -2;
     if (!X) return -3;
     if (!offs || C <= 0) return -4;
@@ -929,8 +955,7 @@ extern "C" int cgp_ei_argmax_pruned(cgp_handle* hh, int kind, const double* X, c
                                     const double* y_std, const double* y_max, const double* Q, const int64_t* qlabel,
                                     int64_t m, int64_t idx_base, double* best_score, int64_t* best_idx,
                                     int64_t* best_cluster, void* workspace, size_t ws_bytes, void* stream) {
-    HandleImpl* h = static_cast<HandleImpl*>(hh);
-    if (!h) return -1;
+    CGP_ENTER(hh);
     if (kind != 0 && kind != 1) return -2;
     if (!X) return -3;
     if (!offs || C <= 0) return -4;
@@ -954,8 +979,7 @@ extern "C" int cgp_ei_argmax_pruned(cgp_handle* hh, int kind, const double* X, c
 
 extern "C" int cgp_rowdot(cgp_handle* hh, const double* A, const double* B, int64_t rows, int64_t n, int64_t ld, double* out,
                           void* stream) {
-    HandleImpl* h = static_cast<HandleImpl*>(hh);
-    if (!h) return -1;
+    CGP_ENTER(hh);
     if (!A) return -2;
     if (!B) return -3;
     if (rows < 0) return -4;
@@ -973,8 +997,7 @@ extern "C" int cgp_rowdot(cgp_handle* hh, const double* A, const double* B, int6
 extern "C" int cgp_argmax_sorted(cgp_handle* hh, const double* score_sorted, int64_t m, const int64_t* perm, const int64_t* coff,
                                  int C, int64_t idx_base, double* best_score, int64_t* best_idx, int64_t* best_cluster,
                                  void* scratch, size_t scratch_bytes, void* stream) {
-    HandleImpl* h = static_cast<HandleImpl*>(hh);
-    if (!h) return -1;
+    CGP_ENTER(hh);
     if (!score_sorted) return -2;
     if (m <= 0) return -3;
     if (!perm) return -4;

@@ -107,6 +107,9 @@ class ClusterGPEngine:
         free, _total = torch.cuda.mem_get_info(self.device)
         budget = int((free + have) * self.mem_fraction)
         want = min(nbytes, budget)
+        if want < nbytes and not partial_ok:
+            raise _lib.CgpError(f"out of device memory: this call needs a {nbytes / 2**30:.2f} GiB workspace, the budget is "
+                                f"{budget / 2**30:.2f} GiB (mem_fraction={self.mem_fraction} of the free memory)")
         if want > have:
             self._ws = None
             self._ws = torch.empty(want, dtype=torch.uint8, device=self.device)
@@ -156,7 +159,7 @@ class ClusterGPEngine:
         if want_grad:
             slot["grad_h"][:B].copy_(out[1], non_blocking=True)
         slot["info_h"][:B].copy_(out[2], non_blocking=True)
-        slot["ev"].record()
+        slot["ev"].record(torch.cuda.current_stream(self.device))
         return slot, B, want_grad
 
     def lml_grad_collect(self, ticket):
@@ -313,6 +316,32 @@ class ClusterGPEngine:
         if not 0 <= c < self.C:
             raise ValueError("label must be an existing cluster id (a new cluster needs a full refit)")
         x = np.asarray(x, dtype=np.float64).reshape(1, self.d)
+        # everything below replaces attributes instead of mutating them, except the new factor row (written in place
+        # into the identity pad) -> a failure (non-PD, out of memory, ...) restores this snapshot: no half-updated engine
+        keep = ("X_host", "y_host", "labels_host", "order", "n", "counts", "offs", "yn_host", "Xs", "yn", "X_orig",
+                "labels_dev", "y_mean_dev", "y_std_dev", "y_max_dev", "npad", "moff")
+        snap = {k: getattr(self, k) for k in keep}
+        snap_stats = (self.y_mean.copy(), self.y_std.copy(), self.y_max.copy())
+        snap_model = dict(self.model)
+        try:
+            return self._append(x, y, c)
+        except BaseException:
+            for k, v in snap.items():
+                setattr(self, k, v)
+            self.y_mean, self.y_std, self.y_max = snap_stats
+            same_buffers = self.model["L"] is snap_model["L"]
+            self.model.clear()
+            self.model.update(snap_model)
+            if same_buffers:  # the kernels may have written row n_c of the cluster's L / W block: back to identity pad
+                npd, row = int(self.npad[c]), int(self.counts[c])
+                if row < npd:
+                    for key in ("L", "W"):
+                        blk = self.model[key][self.moff[c]:self.moff[c + 1]].view(npd, npd)
+                        blk[row].zero_()
+                        blk[row, row] = 1.0
+            raise
+
+    def _append(self, x, y, c):
         dev = self.device
         m = self.model
         old_offs, old_npad, old_moff = self.offs.copy(), self.npad.copy(), self.moff.copy()
@@ -327,6 +356,7 @@ class ClusterGPEngine:
         self.offs = np.concatenate([[0], np.cumsum(self.counts)]).astype(np.int64)
         # targets of cluster c: new statistics, re-normalised (same code path as __init__)
         seg = self.y_host[self.order[self.offs[c]:self.offs[c + 1]]]
+        self.y_mean, self.y_std, self.y_max = self.y_mean.copy(), self.y_std.copy(), self.y_max.copy()
         self.y_max[c] = np.max(seg)
         if self._normalize_y:
             mu, sd = np.mean(seg), np.std(seg)
@@ -374,8 +404,10 @@ class ClusterGPEngine:
                 f"The kernel of cluster {c} is not returning a positive definite matrix after appending a sample "
                 f"({int(info.item())}-th leading minor). Try gradually increasing the 'alpha' parameter "
                 "of your GaussianProcessRegressor estimator.")
-        m["lml"][c] = lml[0]
-        m["lml_host"] = m["lml"].cpu().numpy()
+        lml_all = m["lml"].clone()
+        lml_all[c] = lml[0]
+        m["lml"] = lml_all
+        m["lml_host"] = lml_all.cpu().numpy()
         m.pop("_mspe", None)
         return self
 

@@ -18,6 +18,27 @@ from scipy.optimize import _lbfgsb
 _INT = np.int64 if HAS_ILP64 else np.int32
 
 
+def _check_scipy():
+    """`_lbfgsb.setulb` is private SciPy API.  The positional signature and the integer task codes used below
+    (task[0] == 3: "FG", 1: "NEW_X", ln_task, no iprint/csave) are those of the C port shipped since SciPy 1.15
+    (SP/optimize/_lbfgsb_py.py:389-461); the Fortran wrapper of older releases takes different arguments.  Fail with a
+    clear message instead of an opaque TypeError deep inside a fit.  Upper bound: the newest release this was run on."""
+    import scipy
+
+    from ._lib import CgpError
+
+    try:
+        major, minor = (int(v) for v in scipy.__version__.split(".")[:2])
+    except ValueError as e:  # pragma: no cover
+        raise CgpError(f"cannot parse the SciPy version {scipy.__version__!r}") from e
+    if not ((1, 15) <= (major, minor) <= (1, 18)):
+        raise CgpError(f"cgp_b200.lbfgs drives scipy.optimize._lbfgsb.setulb with the SciPy 1.15-1.18 calling convention; "
+                       f"found SciPy {scipy.__version__} (pin scipy>=1.15,<1.19)")
+
+
+_check_scipy()
+
+
 class _Run:
     """One L-BFGS-B state machine (the body of _minimize_lbfgsb's while-loop, turned inside out)."""
 
