@@ -1,13 +1,19 @@
 """Headline benchmark: one cGP fit + acquisition iteration (everything after clustering,
-REF/cGP/cGP_constrained.py:287-379) on BASELINE.json configs[2]:
-synthetic 6-D piecewise function, n = 32768 in 8 clusters, 16 L-BFGS restarts, 4M EI candidates.
+REF/cGP/cGP_constrained.py:287-379).  Default workload = BASELINE.json configs[2]: synthetic 6-D piecewise function,
+n = 32768 in 8 clusters, 16 L-BFGS restarts, 4M EI candidates.
 
     python bench.py --gpus 1 --steps 2 --warmup 3            # B200 arm (one process per GPU under torchrun for N>1)
     python bench.py --impl reference --steps 2 --warmup 1    # reference arm: scikit-learn/LAPACK on the host cores
+    python bench.py --preset cfg2|cfg4|cfg5|small            # the other BASELINE.json configs
 
-A "step" = ClusterGPEngine(X, y, labels) -> fit (all clusters x 17 runs, lock-step L-BFGS-B) -> k-NN routing ->
-predictive mean/variance -> EI -> argmax -> (N>1) all-gather of maxima + broadcast of the selected point.
+A "step" = the reference-facing call sequence on one batch of inputs:
+    CGPRegressor(...).fit(X, y, labels)   all clusters x (R+1) runs, lock-step L-BFGS-B, final factorisation
+    .select_next(Q, sharded=True)         k-NN routing -> predictive mean/variance -> EI -> argmax
+                                          -> (N>1) all-gather of maxima + broadcast of the selected point
+The acquisition is the exact bound-pruned scan (the default of the public API: same selected candidate and score bits
+as scoring every candidate); the exhaustive scan is timed beside it, outside the timed region.
 metric value = candidates scanned per second of WHOLE iteration time (fit included); strong scaling.
+`value`: candidate shard resident in HBM;  `e2e`: the same calls fed from pinned HOST buffers (H2D inside the region).
 """
 from __future__ import annotations
 
@@ -23,6 +29,8 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+from tools import workloads as W  # noqa: E402
+
 _REAL_STDOUT = None
 
 
@@ -36,28 +44,47 @@ def emit(line):
         os.write(_REAL_STDOUT, data)
 
 
-METRIC = "cGP fit+acq iteration (n=32k, 8 clusters, 16 restarts, 4M EI candidates): EI candidates/sec"
 UNIT = "candidates/s"
-# Total LML+grad evaluations of one config-3 fit (8 clusters x 17 L-BFGS-B runs), measured by the B200 arm
-# (engine.fit_stats["evals"]); the optimiser is SciPy's own setulb fed by LML/gradients that agree with
-# scikit-learn to ~1e-10, so the reference performs the same number.  Used only to extrapolate the CPU sample.
-EVALS_PER_FIT_CFG3 = 4938
-
 PRESETS = {
-    "cfg3": dict(n=32768, d=6, C=8, R=16, M=4194304, k=3, name="configs[2]: 6-D piecewise, n=32768, 8 clusters, R=16, M=4194304"),
-    "small": dict(n=4096, d=6, C=4, R=4, M=262144, k=3, name="smoke preset: n=4096, 4 clusters, R=4, M=262144"),
+    "cfg3": dict(d=6, R=16, M=4194304, k=3, metric="cGP fit+acq iteration (n=32k, 8 clusters, 16 restarts, 4M EI candidates): EI candidates/sec",
+                 name="configs[2]: 6-D piecewise, n=32768, 8 clusters, R=16, M=4194304"),
+    "cfg2": dict(d=2, R=20, M=65536, k=3, metric="cGP fit+acq iteration (Schaffer N2, N=2000, DGM4, 20 restarts, 64k EI candidates): EI candidates/sec",
+                 name="configs[1]: Schaffer N2 2-D, N_PILOT=2000, 4 DGM clusters, R=20, M=65536"),
+    "cfg4": dict(d=4, R=7, M=8388608, k=3, max_lockstep=1, mem_fraction=0.9,
+                 metric="cGP iteration, ONE cluster n=65536 (one lock-step of 8 LML+grad evaluations + factorisation + 8M-candidate EI scan): EI candidates/sec",
+                 name="configs[3]: single cluster n=65536, 4-D Matern-3/2, 8 (cluster, restart) pairs x ONE lock-step, M=8388608"),
+    "cfg5": dict(d=8, R=32, M=16777216, k=3, metric="cGP fit+acq iteration (8-D, 64 clusters of ~512, 32 restarts, 16M EI candidates): EI candidates/sec",
+                 name="configs[4]: 8-D, 64 clusters of n_c in [480,544], R=32, M=16777216"),
+    "small": dict(d=6, R=4, M=262144, k=3, metric="cGP fit+acq iteration (smoke preset): EI candidates/sec",
+                  name="smoke preset: n=4096, 4 clusters, R=4, M=262144"),
 }
+EVALS_FILE = os.path.join(ROOT, "profiles", "fit_evals.json")  # LML+grad evaluations per fit, measured by the B200 arm
 
 
-def make_workload(p):
-    """X ~ default_rng(0).uniform[0,1]^6, r = 4[x0>.5]+2[x1>.5]+[x2>.5] (mod C),
-    y = r + sin(2 pi (r+1) sum(x)/6) + 0.01 N(0,1), labels = r, candidates ~ default_rng(1).uniform."""
-    rng = np.random.default_rng(0)
-    X = rng.uniform(size=(p["n"], p["d"]))
-    r = (4 * (X[:, 0] > .5) + 2 * (X[:, 1] > .5) + (X[:, 2] > .5)).astype(np.int64) % p["C"]
-    y = r + np.sin(2 * np.pi * (r + 1) * X.sum(1) / 6) + 0.01 * rng.standard_normal(p["n"])
-    Q = np.random.default_rng(1).uniform(size=(p["M"], p["d"]))
-    return X, y, r, Q
+def make_workload(preset, M=None):
+    """(X, y, labels, Q) of a preset (tools/workloads.py)."""
+    p = PRESETS[preset]
+    M = p["M"] if M is None else M
+    if preset == "cfg3":
+        return W.cfg3(32768, 6, 8, M)
+    if preset == "small":
+        return W.cfg3(4096, 6, 4, M)
+    if preset == "cfg4":
+        return W.cfg4(65536, M)
+    if preset == "cfg5":
+        return W.cfg5(64, M)
+    # cfg2: the DGM4 clustering of [X, y] is the step BEFORE the path (host, REF/cGP/cGP_constrained.py:214-232); its
+    # labels are the committed fixture so that every run and the scikit-learn golden see the same clusters
+    X, y = W.cfg2_samples()
+    lab = np.load(os.path.join(ROOT, "tests", "golden", "cfg2_full.npz"))["labels"].astype(np.int64)
+    return X, y, lab, W.cfg2_candidates(M)
+
+
+def committed_evals(preset):
+    try:
+        return json.load(open(EVALS_FILE))[preset]["evals"]
+    except Exception:  # noqa: BLE001
+        return None
 
 
 # ------------------------------------------------------------------------------------------------ clocks
@@ -120,89 +147,194 @@ def _ref_gpr(d, theta=None, R=0):
                                     optimizer=None if theta is not None else "fmin_l_bfgs_b", n_restarts_optimizer=R)
 
 
-def cpu_sample(p, X, y, labels, Q, evals_per_fit, m_sub=8192, n_eval=1):
-    """Bounded sample of the reference CPU path on this host: `n_eval` LML+gradient evaluations of cluster 0 at
-    full n_c through scikit-learn, plus k-NN routing + predict(return_std) + EI on `m_sub` candidates; extrapolated
-    to the whole iteration (evals_per_fit evaluations spread evenly over clusters; M candidates)."""
+N_CPU_MAX = 8192  # largest cluster the scikit-learn sample is run at (K_gradient alone is n^2 (d+1) doubles)
+
+
+def cpu_sample(preset, X, y, labels, Q, evals_per_fit, m_sub=8192, n_eval=3):
+    """Bounded sample of the reference CPU path on this host with ALL host cores: `n_eval` LML+gradient evaluations of
+    cluster 0 at full n_c through scikit-learn (N_eval = 3), plus k-NN routing + predict(return_std) + EI
+    on `m_sub` candidates; extrapolated to the whole iteration (evals_per_fit evaluations spread over clusters ~ n_c^3;
+    M candidates ~ n_c^2).  Returns (baseline dict, values for the parity block)."""
     import warnings
 
     from sklearn.neighbors import KNeighborsClassifier
-    from threadpoolctl import threadpool_info
+    from threadpoolctl import threadpool_info, threadpool_limits
 
     import oracle
 
+    p = PRESETS[preset]
     d = p["d"]
     theta = np.array([-0.7] * d + [-4.0])
-    t_eval = []
     sizes = np.bincount(labels)
     c0 = 0
     Xt, yt = X[labels == c0], y[labels == c0].reshape(-1, 1)
-    g = _ref_gpr(d, theta)
-    with warnings.catch_warnings():
+    n_full = Xt.shape[0]
+    scaled = n_full > N_CPU_MAX
+    if scaled:  # configs[3]: scikit-learn cannot allocate its 172 GB K_gradient at n = 65536
+        Xt, yt = Xt[:N_CPU_MAX], yt[:N_CPU_MAX]
+    ncores = os.cpu_count() or 1
+    # torchrun exports OMP_NUM_THREADS=1 to its workers: lift the BLAS pools to every host core explicitly
+    with threadpool_limits(limits=ncores), warnings.catch_warnings():
         warnings.simplefilter("ignore")
+        g = _ref_gpr(d, theta)
         g.fit(Xt, yt)
+        t_eval, val = [], None
         for _ in range(n_eval):
             t0 = time.perf_counter()
-            g.log_marginal_likelihood(theta + 0.01, eval_gradient=True)
+            val = g.log_marginal_likelihood(theta + 0.01, eval_gradient=True)
             t_eval.append(time.perf_counter() - t0)
-    clf = KNeighborsClassifier(n_neighbors=p["k"]).fit(X, labels)
-    Qs = Q[:m_sub]
-    t0 = time.perf_counter()
-    lab = clf.predict(Qs)
-    t_knn = time.perf_counter() - t0
-    t0 = time.perf_counter()
-    mu, sd = g.predict(Qs, return_std=True)
-    oracle.ei_scores(mu, sd, float(yt.max()), Xt.shape[0])
-    t_pred = time.perf_counter() - t0
-    # cost model: LML eval ~ n_c^3, predict ~ n_c^2 per candidate; clusters here are equal-sized to +-2 %
+        clf = KNeighborsClassifier(n_neighbors=p["k"]).fit(X, labels)
+        Qs = Q[:m_sub]
+        t0 = time.perf_counter()
+        lab = clf.predict(Qs)
+        t_knn = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        mu, sd = g.predict(Qs, return_std=True)
+        ei = oracle.ei_scores(np.asarray(mu).reshape(-1), sd, float(yt.max()), Xt.shape[0])
+        t_pred = time.perf_counter() - t0
+        threads = max([int(i.get("num_threads", 1)) for i in threadpool_info()] + [1])
+    n_s = Xt.shape[0]
     s_eval = float(np.mean(t_eval))
-    scale3 = float(np.mean((sizes / sizes[c0]) ** 3))
-    scale2 = float(np.sum((sizes / sizes[c0]) ** 2 * (np.bincount(lab, minlength=len(sizes)) / max(len(lab), 1))))
+    scale3 = float(np.mean((sizes / n_s) ** 3))
+    scale2 = float(np.sum((sizes / n_s) ** 2 * (np.bincount(lab, minlength=len(sizes)) / max(len(lab), 1))))
     fit_s = s_eval * evals_per_fit * scale3
     acq_s = (t_knn + t_pred * max(scale2, 1e-9)) * (p["M"] / m_sub)
-    threads = max([int(i.get("num_threads", 1)) for i in threadpool_info()] + [1])
-    return dict(value=p["M"] / (fit_s + acq_s), unit=UNIT, cores=threads, host_cpus=os.cpu_count(),
-                s_per_lml_grad_eval=s_eval, knn_s=t_knn, predict_ei_s=t_pred, fit_s_extrapolated=fit_s,
-                acq_s_extrapolated=acq_s, iteration_s_extrapolated=fit_s + acq_s,
-                sample=(f"{n_eval} sklearn log_marginal_likelihood(eval_gradient=True) at n_c={Xt.shape[0]} x "
-                        f"{evals_per_fit} evaluations/fit (count measured by the B200 arm, same SciPy L-BFGS-B) + "
-                        f"KNeighborsClassifier.predict / GPR.predict(return_std) / EI on {m_sub} of {p['M']} candidates, "
-                        "extrapolated linearly"))
+    base = dict(value=p["M"] / (fit_s + acq_s), unit=UNIT, cores=threads, host_cpus=ncores, extrapolated=True,
+                s_per_lml_grad_eval=s_eval, n_lml_grad_evals_timed=n_eval, knn_s=t_knn, predict_ei_s=t_pred,
+                fit_s_extrapolated=fit_s, acq_s_extrapolated=acq_s, iteration_s_extrapolated=fit_s + acq_s,
+                evals_per_fit=evals_per_fit,
+                sample=(f"{n_eval} sklearn log_marginal_likelihood(eval_gradient=True) at n_c={n_s}"
+                        + (f" (cluster of {n_full} truncated: K_gradient does not fit; scaled by (n/{n_s})^3)" if scaled else "")
+                        + f" x {evals_per_fit} evaluations/fit (profiles/fit_evals.json, measured by the B200 arm, same SciPy "
+                        f"L-BFGS-B) + KNeighborsClassifier.predict / GPR.predict(return_std) / EI on {m_sub} of {p['M']} "
+                        "candidates, extrapolated linearly; the reference itself runs ONE trust-constr EI search per "
+                        "cluster instead of a dense scan, so this is the CPU cost of the SAME dense-scan iteration"))
+    vals = dict(theta=theta + 0.01, theta_fit=theta, lml=float(val[0]), grad=np.asarray(val[1]), labels=lab,
+                mean=np.asarray(mu).reshape(-1), std=np.asarray(sd), ei=ei, c0=c0, m_sub=m_sub, truncated=scaled, n_s=n_s)
+    return base, vals
 
 
-def run_reference(args, p):
+def cpu_full_iteration(preset, X, y, labels, Q):
+    """The WHOLE iteration through scikit-learn, nothing extrapolated (feasible for configs[1] and the smoke preset):
+    per cluster GaussianProcessRegressor.fit with R restarts (REF/cGP/cGP_constrained.py:315-327), k-NN routing of all
+    M candidates, predict(return_std) + EI + the reference winner rule (:376-378).  -> (seconds, selected index)."""
+    import warnings
+
+    from sklearn.neighbors import KNeighborsClassifier
+    from threadpoolctl import threadpool_limits
+
+    import oracle
+
+    p = PRESETS[preset]
+    t0 = time.perf_counter()
+    with threadpool_limits(limits=os.cpu_count() or 1), warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        clf = KNeighborsClassifier(n_neighbors=p["k"]).fit(X, labels)
+        gprs = []
+        for c in range(int(labels.max()) + 1):
+            gprs.append(_ref_gpr(p["d"], None, p["R"]).fit(X[labels == c], y[labels == c].reshape(-1, 1)))
+        t_fit = time.perf_counter() - t0
+        qlab = clf.predict(Q)
+        best = (-np.inf, -1)
+        for c, g in enumerate(gprs):
+            sel = np.nonzero(qlab == c)[0]
+            if not len(sel):
+                continue
+            mu, sd = g.predict(Q[sel], return_std=True)
+            sc = oracle.ei_scores(np.asarray(mu).reshape(-1), sd, float(y[labels == c].max()), int(np.sum(labels == c)))
+            j = int(np.argmax(sc))
+            if sc[j] > best[0]:
+                best = (float(sc[j]), int(sel[j]))
+    return time.perf_counter() - t0, t_fit, best
+
+
+def run_reference(args, preset):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    X, y, labels, Q = make_workload(p)
-    vals = []
-    last = None
+    p = PRESETS[preset]
+    if args.measured:
+        if preset not in ("cfg2", "small"):
+            raise SystemExit("--measured runs the whole scikit-learn iteration: only feasible for cfg2 / small")
+        X, y, labels, Q = make_workload(preset)
+        ts = [cpu_full_iteration(preset, X, y, labels, Q) for _ in range(args.warmup + args.steps)][args.warmup:]
+        it = float(np.mean([t[0] for t in ts]))
+        v = p["M"] / it
+        cpu = dict(value=v, unit=UNIT, cores=os.cpu_count(), kind="reference", extrapolated=False, iteration_s=it,
+                   fit_s=float(np.mean([t[1] for t in ts])), selected_idx=ts[-1][2][1], selected_score=ts[-1][2][0],
+                   sample="the WHOLE iteration measured: GaussianProcessRegressor.fit per cluster (R restarts) + "
+                          "KNeighborsClassifier.predict + predict(return_std) + EI over all M candidates")
+        emit({"impl": "reference", "metric": p["metric"], "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+              "warmup": args.warmup, "ms_per_step": it * 1e3, "higher_is_better": True, "scaling": "strong",
+              "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": {"workload": p["name"]},
+              "timing": "host wall clock, whole iteration, all host cores", "cpu_baseline": cpu,
+              "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+        return
+    X, y, labels, Q = make_workload(preset, M=16384)
+    evals = committed_evals(preset) or 17 * (int(labels.max()) + 1) * 30
+    vals, last = [], None
     for i in range(args.warmup + args.steps):
-        last = cpu_sample(p, X, y, labels, Q, EVALS_PER_FIT_CFG3 if args.preset == "cfg3" else 17 * p["C"] * 30,
-                          m_sub=4096 if i < args.warmup else 8192)
+        last, _ = cpu_sample(preset, X, y, labels, Q, evals, m_sub=4096 if i < args.warmup else 8192,
+                             n_eval=1 if i < args.warmup else 3)
         if i >= args.warmup:
             vals.append(last["iteration_s_extrapolated"])
     it = float(np.mean(vals))
     v = p["M"] / it
     last["kind"] = "reference"
     last["value"] = v
-    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+    line = {"impl": "reference", "metric": p["metric"], "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": it * 1e3, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": p["name"], "timing": "host wall clock of a bounded sample, extrapolated (see cpu_baseline.sample)"},
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": {"workload": p["name"]},
+            "timing": "host wall clock of a bounded sample on all host cores, extrapolated (see cpu_baseline.sample)",
             "cpu_baseline": last,
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
 
 
+# ------------------------------------------------------------------------------------------------ parity block
+def parity_block(preset, X, y, labels, Q, ref, dev):
+    """GPU vs scikit-learn at FULL cluster size on the same theta (cluster 0, the `m_sub`-candidate subsample of the
+    CPU leg): the numbers REF/cGP/cGP_constrained.py:315-327 / acquisition.py:12-27 would produce."""
+    import torch
+
+    from cgp_b200.engine import ClusterGPEngine
+
+    p = PRESETS[preset]
+    c0, m = ref["c0"], ref["m_sub"]
+    Xt, yt = X[labels == c0][:ref["n_s"]], y[labels == c0][:ref["n_s"]]
+    eng = ClusterGPEngine(Xt, yt, np.zeros(Xt.shape[0], dtype=np.int64), "matern32", 1e-5, device=dev.index,
+                          mem_fraction=p.get("mem_fraction", 0.6))
+    lml, grad, info = eng.lml_grad([0], ref["theta"][None, :], True)
+    out = {"n_c": int(Xt.shape[0]), "candidates": int(m), "truncated_cluster": bool(ref["truncated"]),
+           "lml_rel": abs(lml[0] - ref["lml"]) / abs(ref["lml"]),
+           "grad_rel_scale": float(np.max(np.abs(grad[0] - ref["grad"])) / max(1.0, np.max(np.abs(ref["grad"]))))}
+    eng.set_theta(ref["theta_fit"][None, :])
+    Qs = torch.from_numpy(np.ascontiguousarray(Q[:m])).to(dev)
+    zl = torch.zeros(m, dtype=torch.int64, device=dev)
+    (bs, bi, _), (score, mean, std) = eng.ei_scan(Qs, p["k"], want_arrays=True, qlabel=zl)
+    mean, std, score = mean.cpu().numpy(), std.cpu().numpy(), score.cpu().numpy()
+    out["mean_rel"] = float(np.max(np.abs(mean - ref["mean"]) / np.maximum(np.abs(ref["mean"]), 1e-3)))  # |mean| floored at 1e-3
+    out["var_rel"] = float(np.max(np.abs(std ** 2 - ref["std"] ** 2) / ref["std"] ** 2))
+    out["ei_abs"] = float(np.max(np.abs(score - ref["ei"])))
+    out["same_argmax_on_subsample"] = bool(int(bi.item()) == int(np.argmax(ref["ei"])))
+    # routing: the whole model's k-NN (all clusters) on the same subsample, bit-exact labels
+    X_dev = torch.from_numpy(np.ascontiguousarray(X)).to(dev)
+    l_dev = torch.from_numpy(np.ascontiguousarray(labels.astype(np.int64))).to(dev)
+    from cgp_b200 import _lib
+
+    got = _lib.knn_labels(X_dev, l_dev, Qs, p["k"], int(labels.max()) + 1).cpu().numpy()
+    out["knn_mismatches"] = int(np.sum(got != ref["labels"]))
+    return {k: (float(f"{v:.3e}") if isinstance(v, float) else v) for k, v in out.items()}
+
+
 # ------------------------------------------------------------------------------------------------ B200 arm
-def run_b200(args, p):
+def run_b200(args, preset):
     import torch
     import torch.distributed as dist
 
-    from cgp_b200 import _lib
-    from cgp_b200.engine import ClusterGPEngine
+    from cgp_b200 import CGPRegressor, _lib
 
+    p = PRESETS[preset]
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -210,28 +342,35 @@ def run_b200(args, p):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    X, y, labels, Q = make_workload(p)
-    lo, hi = (p["M"] * rank) // world, (p["M"] * (rank + 1)) // world
+    X, y, labels, Q = make_workload(preset)
+    M = Q.shape[0]
+    lo, hi = (M * rank) // world, (M * (rank + 1)) // world
     Q_dev = torch.from_numpy(Q[lo:hi]).to(dev)
     Q_pin = torch.from_numpy(Q[lo:hi]).pin_memory()
+    Q_head = Q[:8192].copy()
     del Q
     _lib.handle(local)
     stats = {}
 
-    def step(q_src, from_host):
+    def step(q_src, from_host, prune=True):
         e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
         e[0].record()
         q = q_src.to(dev, non_blocking=True) if from_host else q_src
-        eng = ClusterGPEngine(X, y, labels, "matern32", 1e-5)
-        eng.fit(p["R"], seed=0)
+        model = CGPRegressor("matern32", alpha=1e-5, n_restarts_optimizer=p["R"], random_state=0, n_neighbors=p["k"],
+                             max_lockstep=p.get("max_lockstep"), mem_fraction=p.get("mem_fraction", 0.6))
+        model.fit(X, y, labels)
         e[1].record()
-        x_next, score, idx, cl = eng.select_next(q, k=p["k"], sharded=True)
+        x_next, score, idx = model.select_next(q, sharded=True, prune=prune)
         e[2].record()
         torch.cuda.synchronize()
-        stats.update(fit_s=e[0].elapsed_time(e[1]) * 1e-3, acq_s=e[1].elapsed_time(e[2]) * 1e-3, evals=eng.fit_stats["evals"],
-                     lockstep=eng.fit_stats["lockstep"], eval_s=eng.fit_stats["eval_s"], opt_host_s=eng.fit_stats["optimizer_host_s"], evals_per_cluster=eng.fit_stats["evals_per_cluster"].tolist(), nfev_sorted=sorted(int(v) for v in eng.fit_stats["nfev"]), x_next=x_next.tolist(), score=score, idx=idx, cluster=cl,
-                     sizes=eng.counts.tolist(), lml=eng.model["lml_host"].tolist())
-        stats["_engine"] = eng
+        eng = model.engine_
+        fs = eng.fit_stats
+        stats.update(fit_s=e[0].elapsed_time(e[1]) * 1e-3, acq_s=e[1].elapsed_time(e[2]) * 1e-3, evals=fs["evals"],
+                     lockstep=fs["lockstep"], eval_s=fs["eval_s"], opt_host_s=fs["optimizer_host_s"],
+                     evals_per_cluster=fs["evals_per_cluster"].tolist(), nfev_sorted=sorted(int(v) for v in fs["nfev"]),
+                     x_next=x_next.tolist(), score=score, idx=idx, sizes=eng.counts.tolist(),
+                     lml=eng.model["lml_host"].tolist(), shard_mode=fs["shard_mode"])
+        stats["_model"] = model
         return x_next
 
     def barrier():
@@ -259,7 +398,8 @@ def run_b200(args, p):
         _lib.profile_enable(2 if i == args.warmup - 1 else 0, local)
         step(Q_dev, False)
     _lib.profile_enable(False, local)
-    # fp64 tensor peak measured here (cuBLAS DGEMM through torch; not in MEASURED_PEAKS.json, which has bf16 only)
+    # fp64 tensor peak measured here (cuBLAS DGEMM through torch; MEASURED_PEAKS.json has bf16 only)
+    torch.cuda.empty_cache()
     A = torch.randn((8192, 8192), dtype=torch.float64, device=dev)
     Bm = torch.randn((8192, 8192), dtype=torch.float64, device=dev)
     Cm = torch.empty_like(A)
@@ -281,105 +421,101 @@ def run_b200(args, p):
     sampler.start()
     t_dev, t_wall = timed(args.steps, Q_dev, False)
     clocks = sampler.stop()
-    prof = _lib.profile_read(reset=True, device=local)
+    prof = _lib.profile_read(reset=True, device=local, detail=True)
     _lib.profile_enable(False, local)
     step_s = t_dev / args.steps
     res = dict(stats)
     t_e2e, _ = timed(args.steps, Q_pin, True)
     e2e_s = t_e2e / args.steps
-    # outside every timed region: the exact bound-pruned scan on the same fitted model (reported beside the exhaustive one)
-    eng = stats.pop("_engine")
-    res.pop("_engine", None)
-    barrier()
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
-    _xp, score_p, idx_p, cl_p = eng.select_next(Q_dev, k=p["k"], sharded=True, prune=True)
-    b.record()
-    barrier()
-    tp = torch.tensor([a.elapsed_time(b) * 1e-3], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tp, op=dist.ReduceOp.MAX)
-    pruned = {"acq_s": float(tp[0]), "acq_candidates_per_s": p["M"] / float(tp[0]),
-              "same_selection": bool(idx_p == res["idx"] and score_p == res["score"] and cl_p == res["cluster"]),
-              "note": "cgp_ei_argmax_pruned: mean-only EI bound, survivors scored exactly; NOT used in the timed region"}
-    del eng
+    # outside every timed region: the EXHAUSTIVE scan on the same fitted model (every candidate scored)
+    model = stats.pop("_model")
+    res.pop("_model", None)
+    exhaustive = None
+    if not args.no_exhaustive and preset != "cfg4":  # cfg4: 8M x 65536^2 flops = 18 min on one GPU
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        _x, score_f, idx_f = model.select_next(Q_dev, sharded=True, prune=False)
+        b.record()
+        barrier()
+        tp = torch.tensor([a.elapsed_time(b) * 1e-3], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tp, op=dist.ReduceOp.MAX)
+        exhaustive = {"acq_s": float(tp[0]), "acq_candidates_per_s": M / float(tp[0]),
+                      "same_selection": bool(idx_f == res["idx"] and score_f == res["score"])}
+    del model
+    torch.cuda.empty_cache()
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
-    # ---- roofline of the dominant kernel class (CUDA events on the launch stream, inside the timed region)
+    # ---- roofline: per-class exclusive kernel time (events on the launch stream, timed region) and algorithmic flops
+    # tallied by the library for exactly the launches that were timed (include/cgp_b200.h: cgp_profile_flops)
     sizes = np.asarray(res["sizes"], dtype=np.float64)
-    ev_c = np.asarray(res["evals_per_cluster"], dtype=np.float64) * args.steps  # this rank's evaluations, timed region
-    m_local = hi - lo
-    PANEL, TILE = 4, 128
-    alg = {"potrf_trail": 0.0, "trtri_trail": 0.0, "lauum": 0.0, "predict_vnorm": 0.0}
-    for n_c, e_c in zip(sizes, ev_c):
-        T = int(-(-n_c // TILE))
-        for c0 in range(0, T, PANEL):
-            c1 = min(T, c0 + PANEL)
-            nt = max(0.0, n_c - TILE * c1)  # trailing order after this panel
-            K = TILE * (c1 - c0)
-            alg["potrf_trail"] += e_c * K * nt * (nt + 1)  # SYRK: 2 K nt(nt+1)/2
-            ksum = sum(TILE * (c1 - max(j, c0)) for j in range(c1))
-            alg["trtri_trail"] += e_c * 2.0 * nt * TILE * ksum
-        alg["lauum"] += e_c * n_c ** 3 / 3.0
-    alg["predict_vnorm"] = args.steps * m_local * float(np.mean(sizes ** 2))
-    # k_lauum and k_predict_vnorm run alone on the caller's stream: their event brackets are exclusive kernel time.
-    # The trailing-update kernels of the Cholesky / triangular inverse run on three streams at once (chain, bulk,
-    # inverse: look-ahead schedule), so their brackets include the time they share the SMs with the other two streams;
-    # they are listed (overlapped=true) but the roofline kernel is taken from the exclusive ones.
-    exclusive = {"lauum", "predict_vnorm"}
     roof_all = {}
-    for k, fl in alg.items():
-        ms, cnt = prof[k]
-        if ms > 0:
-            roof_all[k] = {"ms": ms, "launches": cnt, "achieved": fl / (ms * 1e-3) / 1e12, "share_of_step": ms * 1e-3 / t_dev,
-                           "overlapped": k not in exclusive}
-    fit_wall = res["fit_s"] * args.steps
-    fit_unit = {"s": fit_wall, "achieved": float(np.sum(ev_c * sizes ** 3)) / fit_wall / 1e12,
-                "note": "whole LML+gradient unit: n_c^3 algorithmic flops per evaluation (potrf + inverse + K^-1) over the "
-                        "fit wall time of the timed region, all kernels, host L-BFGS-B and final factorisation included"}
-    top = max((k for k in roof_all if k in exclusive), key=lambda k: roof_all[k]["ms"])
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tp):
-        traffic = json.load(open(tp)).get(top)
-    roofline = {"bound": "tensor", "kernel": "k_" + top, "achieved": roof_all[top]["achieved"], "peak": fp64_peak,
-                "unit": "TFLOP/s", "frac": roof_all[top]["achieved"] / fp64_peak, "traffic": traffic,
-                "peak_source": "cuBLAS DGEMM 8192^3 fp64 measured in this run (MEASURED_PEAKS.json has no fp64 entry)",
-                "algorithmic_flops": "potrf_trail: K n_t(n_t+1) per rank-K SYRK of the order-n_t trailing block; lauum: n_c^3/3; "
-                                     "trtri_trail: 2 n_t 128 sum_j K_j; predict_vnorm: n_c^2 per candidate",
-                "all": roof_all, "lml_grad_unit": fit_unit}
-    gpu_launches = int(sum(c for _, c in prof.values()))
-    kernel_ms = {k: round(v[0], 3) for k, v in prof.items() if v[1] and v[0] > 0}  # large kernels only (profiling level 2)
-    kernel_launches = {k: v[1] for k, v in prof.items() if v[1]}
-    cpu = None
+    for k, v in prof.items():
+        if v["ms"] > 0 and v["flops"] > 0:
+            roof_all[k] = {"ms": round(v["ms"], 2), "timed_launches": v["timed"], "launches": v["launches"],
+                           "tflops": round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 2),
+                           "frac": round(v["flops"] / (v["ms"] * 1e-3) / 1e12 / fp64_peak, 3),
+                           "share_of_step": round(v["ms"] * 1e-3 / t_dev, 3)}
+    ev_c = np.asarray(res["evals_per_cluster"], dtype=np.float64)  # this rank's evaluations in one step
+    step_flops = float(np.sum(ev_c * sizes ** 3)) + float(np.sum(sizes ** 3)) * 2.0 / 3.0  # fit + final factorisation
+    roofline = None
+    if roof_all:
+        top = max(roof_all, key=lambda k: roof_all[k]["ms"])  # the class with the largest share of the step
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get(top)
+        roofline = {"bound": "tensor", "kernel": "k_" + top, "achieved": roof_all[top]["tflops"], "peak": round(fp64_peak, 2),
+                    "unit": "TFLOP/s", "frac": roof_all[top]["frac"], "traffic": traffic,
+                    "peak_source": "cuBLAS DGEMM 8192^3 fp64 measured in this run (MEASURED_PEAKS.json has no fp64 entry)",
+                    "choice": "class with the largest exclusive time in the timed region; batches <= CGP_FORK_MAX matrices "
+                              "(three-stream schedule) are counted but not timed",
+                    "classes": roof_all,
+                    "step": {"algorithmic_flops": step_flops, "note": "n_c^3 per LML+grad evaluation (potrf + inverse + K^-1) "
+                             "+ 2/3 n_c^3 per final factorisation, rank 0; over the whole iteration incl. host L-BFGS-B and the scan",
+                             "tflops": round(step_flops / step_s / 1e12, 2), "frac": round(step_flops / step_s / 1e12 / fp64_peak, 3),
+                             "fit_only_frac": round(step_flops / res["fit_s"] / 1e12 / fp64_peak, 3)}}
+    gpu_launches = int(sum(v["launches"] for v in prof.values()))
+    cpu = parity = None
+    evals_file = committed_evals(preset)
     if world == 1 and not args.no_cpu_baseline:
-        Xw, yw, lw, Qw = make_workload(p)
-        cpu = cpu_sample(p, Xw, yw, lw, Qw, res["evals"])
+        Xw, yw, lw, _ = make_workload(preset, M=0)
+        cpu, refvals = cpu_sample(preset, Xw, yw, lw, Q_head, res["evals"])
         cpu["kind"] = "port"
         cpu["note"] = ("scikit-learn 1.9.0 / SciPy / OpenBLAS objects configured exactly as the reference does "
                        "(the arithmetic the reference delegates to) + oracle EI restatement")
-    line = {"metric": METRIC, "value": p["M"] / step_s, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        parity = parity_block(preset, Xw, yw, lw, Q_head, refvals, dev)
+    line = {"metric": p["metric"], "value": M / step_s, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": p["name"], "parallelism": f"pairs+candidates sharded over {world} GPU(s)",
-                       "l2": "working set (36 GB of factor workspaces, 1 GB K* chunks) >> 126 MB L2; no flush needed",
-                       "timing": "CUDA events around K whole steps, barrier+synchronize both sides, max over ranks"},
-            "iteration_s": step_s, "fit_s": res["fit_s"], "acq_s": res["acq_s"],
-            "acq_candidates_per_s": p["M"] / res["acq_s"], "lml_evals_per_fit_rank0": res["evals"],
-            "lockstep_per_fit": res["lockstep"], "fit_eval_wall_s": res["eval_s"], "fit_optimizer_host_s": res["opt_host_s"], "nfev_per_pair_rank0_sorted": res["nfev_sorted"], "selected": {"idx": res["idx"], "score": res["score"], "cluster": res["cluster"],
-                                                              "x": res["x_next"]},
-            "wall_s_per_step": t_wall / args.steps,
-            "e2e": {"value": p["M"] / e2e_s, "unit": UNIT,
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": {"workload": p["name"]},
+            "fit_s": round(res["fit_s"], 4), "acq_s": round(res["acq_s"], 4),
+            "selected": {"idx": res["idx"], "score": res["score"], "x": [round(v, 6) for v in res["x_next"]]},
+            "parity": parity,
+            "e2e": {"value": M / e2e_s, "unit": UNIT,
                     "h2d_bytes_per_step": int(Q_pin.numel() * 8 + X.nbytes + y.nbytes + labels.nbytes),
                     "d2h_bytes_per_step": int((p["d"] + 2) * 8), "ms_per_step": e2e_s * 1e3},
-            "acq_pruned_scan": pruned,
-            "gpu_launches": gpu_launches, "kernel_launches_timed_region": kernel_launches,
-            "kernel_ms_timed_region": kernel_ms,
-            "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks}
+            "gpu_launches": gpu_launches, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
+            "acq": "exact bound-pruned scan (public default)", "acq_exhaustive_scan": exhaustive,
+            "acq_candidates_per_s": M / res["acq_s"], "lml_evals_per_fit_rank0": res["evals"],
+            "lml_evals_committed": evals_file, "lockstep_per_fit": res["lockstep"], "shard_mode": res["shard_mode"],
+            "fit_eval_wall_s": round(res["eval_s"], 4), "fit_optimizer_host_s": round(res["opt_host_s"], 4),
+            "wall_s_per_step": t_wall / args.steps,
+            "parallelism": f"(cluster, restart) runs + candidates sharded over {world} GPU(s)",
+            "l2": "working set (factor workspaces of tens of GB, 1 GB K* chunks) >> 126 MB L2; no flush needed",
+            "timing": "CUDA events around K whole steps, barrier+synchronize both sides, max over ranks"}
     emit(line)
+    detail = {"preset": preset, "n_gpus": world, "nfev_per_pair_rank0_sorted": res["nfev_sorted"],
+              "evals_per_cluster_rank0": res["evals_per_cluster"], "sizes": res["sizes"], "lml": res["lml"],
+              "kernel_classes": prof}
+    try:
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        json.dump(detail, open(os.path.join(ROOT, "gpurun_out", f"bench_detail_{preset}_n{world}.json"), "w"))
+    except OSError:
+        pass
     if world > 1:
         dist.destroy_process_group()
 
@@ -392,16 +528,18 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--preset", default="cfg3", choices=sorted(PRESETS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-exhaustive", action="store_true")
+    ap.add_argument("--measured", action="store_true",
+                    help="reference arm: run the WHOLE scikit-learn iteration instead of an extrapolated sample (cfg2 / small)")
     args = ap.parse_args()
-    p = PRESETS[args.preset]
     global _REAL_STDOUT
     sys.stdout.flush()
     _REAL_STDOUT = os.dup(1)
     os.dup2(2, 1)
     if args.impl == "reference":
-        run_reference(args, p)
+        run_reference(args, args.preset)
     else:
-        run_b200(args, p)
+        run_b200(args, args.preset)
 
 
 if __name__ == "__main__":

@@ -53,6 +53,7 @@ SIGNATURES = {
     "cgp_profile_class_name": (C.c_char_p, [C.c_int]),
     "cgp_profile_enable": (C.c_int, [_vp, C.c_int]),
     "cgp_profile_read": (C.c_int, [_vp, C.POINTER(C.c_double), _pi64, C.c_int, C.c_int]),
+    "cgp_profile_flops": (C.c_int, [_vp, C.POINTER(C.c_double), _pi64, C.c_int]),
 }
 
 _lib = None
@@ -334,11 +335,20 @@ def profile_enable(on=True, device=None):
     _chk(lib().cgp_profile_enable(handle(device), int(on)), "cgp_profile_enable")
 
 
-def profile_read(reset=True, device=None):
-    """-> {class name: (milliseconds, launches)} accumulated since the last reset (synchronises)."""
+def profile_read(reset=True, device=None, detail=False):
+    """-> {class name: (milliseconds, launches)} accumulated since the last reset (synchronises).
+    detail=True: {class: dict(ms, launches, timed, flops)} — ms / flops / timed cover the launches that were bracketed by
+    events (exclusive kernel time: batches on the three-stream schedule are counted in `launches` but not timed)."""
     L = lib()
     n = L.cgp_profile_classes()
     ms = (C.c_double * n)()
     cnt = (C.c_int64 * n)()
+    fl = (C.c_double * n)()
+    timed = (C.c_int64 * n)()
+    if detail:
+        _chk(L.cgp_profile_flops(handle(device), fl, timed, n), "cgp_profile_flops")
     _chk(L.cgp_profile_read(handle(device), ms, cnt, n, 1 if reset else 0), "cgp_profile_read")
-    return {L.cgp_profile_class_name(i).decode(): (float(ms[i]), int(cnt[i])) for i in range(n)}
+    names = [L.cgp_profile_class_name(i).decode() for i in range(n)]
+    if detail:
+        return {names[i]: dict(ms=float(ms[i]), launches=int(cnt[i]), timed=int(timed[i]), flops=float(fl[i])) for i in range(n)}
+    return {names[i]: (float(ms[i]), int(cnt[i])) for i in range(n)}

@@ -15,7 +15,7 @@ from .gpr import GaussianProcessRegressor, KNeighborsClassifier, parse_kernel
 
 class CGPRegressor:
     def __init__(self, kernel=None, *, alpha=1e-5, n_restarts_optimizer=None, normalize_y=True, random_state=0,
-                 n_neighbors=3, optimizer="fmin_l_bfgs_b"):
+                 n_neighbors=3, optimizer="fmin_l_bfgs_b", max_lockstep=None, mem_fraction=0.6):
         self.kernel = kernel
         self.alpha = alpha
         self.n_restarts_optimizer = n_restarts_optimizer  # None -> 10*d, REF/cGP/cGP_constrained.py:316
@@ -23,6 +23,8 @@ class CGPRegressor:
         self.random_state = random_state
         self.n_neighbors = n_neighbors
         self.optimizer = optimizer
+        self.max_lockstep = max_lockstep  # None: run every L-BFGS-B run to convergence (engine.fit)
+        self.mem_fraction = mem_fraction  # share of the free device memory the factor workspaces may take
 
     def fit(self, X, y, labels):
         X = np.asarray(X, dtype=np.float64)
@@ -31,8 +33,9 @@ class CGPRegressor:
         d = X.shape[1]
         kind, theta0, bounds, template = parse_kernel(self.kernel, d)
         R = 10 * d if self.n_restarts_optimizer is None else int(self.n_restarts_optimizer)
-        eng = ClusterGPEngine(X, y, labels, kind, self.alpha, self.normalize_y)
-        eng.fit(R, seed=self.random_state, theta0=theta0, bounds=bounds, optimize=self.optimizer is not None)
+        eng = ClusterGPEngine(X, y, labels, kind, self.alpha, self.normalize_y, mem_fraction=self.mem_fraction)
+        eng.fit(R, seed=self.random_state, theta0=theta0, bounds=bounds, optimize=self.optimizer is not None,
+                max_lockstep=self.max_lockstep)
         self.engine_ = eng
         self._template = template
         self._bounds = bounds
@@ -88,10 +91,10 @@ class CGPRegressor:
         return dict(labels=ql.cpu().numpy(), mean=mean.cpu().numpy(), std=std.cpu().numpy(), score=score.cpu().numpy(),
                     best_score=float(bs.item()), best_idx=int(bi.item()), best_cluster=int(bc.item()))
 
-    def select_next(self, candidates, sharded=False, prune=False):
-        """-> (x_next [d], score, idx).  Multi-GPU aware (see cgp_b200/dist.py).  prune=True: exact bound-pruned scan,
-        same selection (candidates whose EI bound from the predictive mean cannot reach the running best skip the
-        variance contraction)."""
+    def select_next(self, candidates, sharded=False, prune=True):
+        """-> (x_next [d], score, idx).  Multi-GPU aware (see cgp_b200/dist.py).  prune=True (default): exact bound-pruned
+        scan, same selection and score bits (candidates whose EI bound from the predictive mean cannot reach the running
+        best skip the variance contraction); prune=False: exhaustive scan."""
         x, score, idx, _cl = self.engine_.select_next(candidates, self.n_neighbors, sharded=sharded, prune=prune)
         return x, score, idx
 

@@ -37,6 +37,7 @@ static const char* const kClassNames[CLS_COUNT] = {
 struct ProfRec {
     cudaEvent_t a, b;
     int cls;
+    double flops;  // algorithmic flops of the bracketed launch (0 when not tallied)
 };
 
 struct HandleImpl : cgp_handle {
@@ -45,10 +46,15 @@ struct HandleImpl : cgp_handle {
     // per-kernel-class launch counters (always) and CUDA-event timing (when enabled)
     int prof_on;      // 0 off, 1 every launch bracketed by events, 2 only the large kernels the roofline is quoted for
     bool prof_skip;   // the launch in flight is counted but not timed
+    bool prof_mute;   // inside a forked (three-stream) batch: brackets would overlap other streams -> count only
     std::vector<ProfRec> recs;
     size_t recs_used;
     double ms[CLS_COUNT];
+    double flops[CLS_COUNT];       // algorithmic flops of the TIMED launches of each class (roofline numerator)
+    double pending_flops;          // set by FL() for the next KL launch
     long long launches[CLS_COUNT];
+    long long timed[CLS_COUNT];    // launches that were bracketed by events
+    int fork_max;  // batches with more matrices than this run the one-stream schedule (CGP_FORK_MAX, default 24)
     // internal streams of run_pipeline: sc (high priority) = the dependent chain update -> diag -> panel + look-ahead part
     // of the trailing update; s2 (low priority) = triangular-inverse work of panel p beside the Cholesky of panel p+1.
     // The caller's stream carries the bulk trailing updates and everything else; all three are joined before return.
@@ -60,7 +66,10 @@ struct HandleImpl : cgp_handle {
 
 static inline void prof_begin(HandleImpl* h, int cls, cudaStream_t s) {
     h->launches[cls]++;
-    if (!h->prof_on) return;
+    if (!h->prof_on || h->prof_mute) {
+        h->prof_skip = true;
+        return;
+    }
     // level 2: the event pair costs ~2 x 1.5 us of stream latency per launch, which is visible on the latency-bound
     // chain of small kernels (diag / panel / update ...) when few matrices are in flight; time only the big ones.
     h->prof_skip = h->prof_on == 2 && !(cls == CLS_LAUUM || cls == CLS_PREDICT_VNORM || cls == CLS_POTRF_TRAIL ||
@@ -75,9 +84,11 @@ static inline void prof_begin(HandleImpl* h, int cls, cudaStream_t s) {
     }
     ProfRec& r = h->recs[h->recs_used];
     r.cls = cls;
+    r.flops = h->pending_flops;
     cudaEventRecord(r.a, s);
 }
 static inline void prof_end(HandleImpl* h, cudaStream_t s) {
+    h->pending_flops = 0.0;
     if (!h->prof_on || h->prof_skip) return;
     cudaEventRecord(h->recs[h->recs_used].b, s);
     h->recs_used++;
@@ -89,6 +100,9 @@ static inline void prof_end(HandleImpl* h, cudaStream_t s) {
         __VA_ARGS__;          \
         prof_end(h, s);       \
     } while (0)
+
+// FL(h, flops): algorithmic flops of the NEXT KL launch (tallied only if that launch is timed)
+#define FL(h, f) ((h)->pending_flops = (double)(f))
 
 // Every entry point that launches work runs on the handle's device, whatever the caller's current device is, and
 // restores the caller's device on return.
@@ -198,7 +212,13 @@ extern "C" int cgp_create(cgp_handle** out, int device) {
     h->prof_on = 0;
     h->prof_skip = false;
     h->recs_used = 0;
-    for (int i = 0; i < CLS_COUNT; ++i) h->ms[i] = 0.0, h->launches[i] = 0;
+    for (int i = 0; i < CLS_COUNT; ++i) h->ms[i] = 0.0, h->launches[i] = 0, h->flops[i] = 0.0, h->timed[i] = 0;
+    h->pending_flops = 0.0;
+    h->prof_mute = false;
+    {
+        const char* e = getenv("CGP_FORK_MAX");
+        h->fork_max = e ? atoi(e) : 24;
+    }
     int rc = handle_init(h, device);
     if (rc) {  // nothing leaks when a step of the construction fails
         handle_free(h);
@@ -231,6 +251,8 @@ extern "C" int cgp_profile_read(cgp_handle* hh, double* ms, int64_t* launches, i
         CGP_CHECK(cudaEventSynchronize(h->recs[i].b));
         CGP_CHECK(cudaEventElapsedTime(&t, h->recs[i].a, h->recs[i].b));
         h->ms[h->recs[i].cls] += t;
+        h->flops[h->recs[i].cls] += h->recs[i].flops;
+        h->timed[h->recs[i].cls]++;
     }
     h->recs_used = 0;
     for (int i = 0; i < n_cls && i < CLS_COUNT; ++i) {
@@ -238,7 +260,21 @@ extern "C" int cgp_profile_read(cgp_handle* hh, double* ms, int64_t* launches, i
         if (launches) launches[i] = h->launches[i];
     }
     if (reset)
-        for (int i = 0; i < CLS_COUNT; ++i) h->ms[i] = 0.0, h->launches[i] = 0;
+        for (int i = 0; i < CLS_COUNT; ++i) h->ms[i] = 0.0, h->launches[i] = 0, h->flops[i] = 0.0, h->timed[i] = 0;
+    return 0;
+}
+
+// Algorithmic flops and number of the TIMED launches per class since the last reset (call before the resetting
+// cgp_profile_read).  With profiling on, batches that run the three-stream schedule are counted but not timed (their
+// event brackets would include work of the other two streams), so ms / flops / timed describe exclusive kernel time.
+extern "C" int cgp_profile_flops(cgp_handle* hh, double* flops, int64_t* timed, int n_cls) {
+    CGP_ENTER(hh);
+    int rc = cgp_profile_read(hh, nullptr, nullptr, 0, 0);  // fold finished event pairs
+    if (rc) return rc;
+    for (int i = 0; i < n_cls && i < CLS_COUNT; ++i) {
+        if (flops) flops[i] = h->flops[i];
+        if (timed) timed[i] = h->timed[i];
+    }
     return 0;
 }
 
@@ -344,9 +380,37 @@ struct Batch {
     double *A = nullptr, *U = nullptr, *D = nullptr, *logdet = nullptr, *z = nullptr, *a = nullptr, *gpart = nullptr;
 };
 
-// assemble -> blocked Cholesky -> U = L^-T -> z, a, lml [-> K^-1 -> gradient]
+// ---- algorithmic flop counts of the large launches (roofline numerators; real rows / columns only) ----
+// number of elements (r, c) with a <= c < b and c <= r < n  (lower-triangular part of the columns [a, b))
+static inline double tri_cols(double n, double a, double b) {
+    b = std::min(b, n);
+    return b > a ? (b - a) * (2.0 * n - a - b + 1.0) * 0.5 : 0.0;
+}
+// rank-K update of the lower triangle restricted to the element columns [128 ta, 128 tb): 2 K per element
+static double flops_syrk(const MatMeta* hm, int nm, int c0, int c1, int ta, int tb) {
+    double f = 0.0;
+    for (int i = 0; i < nm; ++i)
+        f += 2.0 * CGP_TILE * (c1 - c0) * tri_cols(hm[i].n, (double)CGP_TILE * ta, (double)CGP_TILE * tb);
+    return f;
+}
+// push of the inverse panel [c0, c1) into the columns >= c1: rows j < c1 (128 each), real columns n - 128 c1,
+// K_j = 128 (c1 - max(j, c0)), the diagonal block U[j,j] (j >= c0) is triangular (half of its 128 k)
+static double flops_trtri_trail(const MatMeta* hm, int nm, int c0, int c1) {
+    double ksum = 0.0;
+    for (int j = 0; j < c1; ++j) ksum += CGP_TILE * (c1 - std::max(j, c0)) - (j >= c0 ? CGP_TILE / 2 : 0);
+    double f = 0.0;
+    for (int i = 0; i < nm; ++i) f += 2.0 * CGP_TILE * std::max(0.0, (double)hm[i].n - (double)CGP_TILE * c1) * ksum;
+    return f;
+}
+static double flops_cube_third(const MatMeta* hm, int nm) {
+    double f = 0.0;
+    for (int i = 0; i < nm; ++i) f += (double)hm[i].n * hm[i].n * hm[i].n / 3.0;
+    return f;
+}
+
+// assemble -> blocked Cholesky -> U = L^-T -> z, a, lml [-> K^-1 -> gradient].   hm: host copy of b.meta
 static int run_pipeline(HandleImpl* h, int kind, const double* X, const double* y, const double* theta, double alpha, int d,
-                        const Batch& b, double* lml, double* grad, int* info, cudaStream_t s) {
+                        const Batch& b, const MatMeta* hm, double* lml, double* grad, int* info, cudaStream_t s) {
     const int nm = b.nm, T = b.Tmax;
     const size_t xs = xtile_smem(d);
     dim3 gl(b.ntl_max, nm);
@@ -362,8 +426,11 @@ static int run_pipeline(HandleImpl* h, int kind, const double* X, const double* 
     // With few matrices in the batch (tail of the L-BFGS lock-step, small share per GPU) the chain leaves most SMs idle;
     // the bulk and inverse launches of the same matrices fill them.  Every tile sees the same sequence of updates as in
     // a single-stream schedule, so results are bit-identical.
+    // Large batches fill the SMs from one stream and run the plain one-stream schedule (fork_max, CGP_FORK_MAX): same
+    // bits, and every event bracket of the profiling levels is then exclusive kernel time.
     const int n_panels = (T + CGP_PANEL - 1) / CGP_PANEL;
-    const bool fork = n_panels > 1;
+    const bool fork = n_panels > 1 && nm <= h->fork_max;
+    h->prof_mute = fork;
     cudaStream_t st = fork ? h->s2 : s;
     cudaStream_t sc = fork ? h->sc : s;
     while ((int)h->panel_ev.size() < 2 * n_panels) {
@@ -393,10 +460,12 @@ static int run_pipeline(HandleImpl* h, int kind, const double* X, const double* 
             const int H = std::min(CGP_PANEL, T - c1);
             if (fork && rest_pending) CGP_CHECK(cudaStreamWaitEvent(sc, h->panel_ev[2 * (p - 1) + 1], 0));
             rest_pending = false;
+            FL(h, flops_syrk(hm, nm, c0, c1, c1, c1 + H));
             GL(CLS_POTRF_TRAIL, sc, k_potrf_head, H * (T - c1), nm, b.A, b.meta, c0, c1, T);
             const int Tr = T - c1 - H;
             if (Tr > 0) {
                 if (fork) CGP_CHECK(cudaStreamWaitEvent(s, h->panel_ev[2 * p], 0));
+                FL(h, flops_syrk(hm, nm, c0, c1, c1 + H, T));
                 GL(CLS_POTRF_TRAIL, s, k_potrf_trail, Tr * (Tr + 1) / 2, nm, b.A, b.meta, c0, c1, c1 + H);
                 if (fork) {
                     CGP_CHECK(cudaEventRecord(h->panel_ev[2 * p + 1], s));
@@ -409,8 +478,10 @@ static int run_pipeline(HandleImpl* h, int kind, const double* X, const double* 
                 GL(CLS_TRTRI_ACC, st, k_trtri_acc, i, nm, b.A, b.U, b.meta, i, c0);
             GLI(CLS_TRTRI_SCALE, st, k_trtri_scale, i, nm, b.U, b.D, b.meta, i);
         }
-        if (c1 < T)
+        if (c1 < T) {
+            FL(h, flops_trtri_trail(hm, nm, c0, c1));
             GL(CLS_TRTRI_TRAIL, st, k_trtri_trail, c1 * (T - c1), nm, b.A, b.U, b.meta, c0, c1, T);
+        }
     }
     if (fork) {
         CGP_CHECK(cudaEventRecord(h->chain_ev, sc));
@@ -418,10 +489,12 @@ static int run_pipeline(HandleImpl* h, int kind, const double* X, const double* 
         CGP_CHECK(cudaEventRecord(h->join_ev, st));
         CGP_CHECK(cudaStreamWaitEvent(s, h->join_ev, 0));
     }
+    h->prof_mute = false;
     KL(h, CLS_SOLVE, s, k_solve_z<<<dim3(T, nm), 1024, 0, s>>>(b.U, y, b.z, b.meta, b.npad_max));
     KL(h, CLS_SOLVE, s, k_solve_a<<<dim3(b.npad_max / 8, nm), 256, 0, s>>>(b.U, b.z, b.a, b.meta, b.npad_max));
     KL(h, CLS_SOLVE, s, k_lml_finish<<<nm, 256, 0, s>>>(b.z, b.logdet, info, lml, b.meta, b.npad_max, T));
     if (grad) {
+        FL(h, flops_cube_third(hm, nm));
         GL(CLS_LAUUM, s, k_lauum, b.ntl_max, nm, b.A, b.U, b.meta);
         const int dm = dmax_for(d);
         const size_t gs = xs + (2 * CGP_TILE + 8 * dm) * 8;
@@ -551,7 +624,7 @@ extern "C" int cgp_lml_grad_batched(cgp_handle* hh, int kind, const double* X, c
         }
         int rc = upload(h, b.meta, &metas[m0], (size_t)(m1 - m0) * sizeof(MatMeta), s);
         if (rc) return rc;
-        rc = run_pipeline(h, kind, X, y, theta, alpha, d, b, lml, grad, info, s);
+        rc = run_pipeline(h, kind, X, y, theta, alpha, d, b, &metas[m0], lml, grad, info, s);
         if (rc) return rc;
         m0 = m1;
     }
@@ -623,7 +696,7 @@ extern "C" int cgp_factorize(cgp_handle* hh, int kind, const double* X, const do
     CGP_CHECK(cudaMemsetAsync(L, 0, (size_t)elems * 8, s));  // strictly-upper tiles are never written by the pipeline
     int rc = upload(h, b.meta, metas.data(), (size_t)C * sizeof(MatMeta), s);
     if (rc) return rc;
-    rc = run_pipeline(h, kind, X, y, theta, alpha, d, b, lml, nullptr, info, s);
+    rc = run_pipeline(h, kind, X, y, theta, alpha, d, b, metas.data(), lml, nullptr, info, s);
     if (rc) return rc;
     KL(h, CLS_TRANSPOSE, s, k_transpose<<<dim3(b.npad_max / 32, b.npad_max / 32, C), dim3(32, 8), 0, s>>>(b.U, W, b.meta));
     KL(h, CLS_SOLVE, s, k_gather_alpha<<<dim3((b.npad_max + 255) / 256, C), 256, 0, s>>>(b.a, alpha_vec, b.meta, b.npad_max));
@@ -882,6 +955,7 @@ static int run_score(HandleImpl* h, int kind, const double* X, const int64_t* of
             }
             // mean-only callers (predict(return_std=False)) skip the n_c^2-per-candidate variance contraction
             const bool need_var = std_ != nullptr || y_max != nullptr;
+            if (need_var) FL(h, (double)rows * (double)n * (double)n);
             if (need_var)
                 KL(h, CLS_PREDICT_VNORM, s, k_predict_vnorm<<<(unsigned)((rows_pad / CGP_TILE) * T), CGP_GEMM_THREADS, GEMM_SMEM_BYTES, s>>>(
                     Wc, kstar, vpart, (int)npad, L.mch));

@@ -43,8 +43,9 @@ class cGP_constrained(object):
         # incremental refit: when the clustering keeps the labels of the old samples, append the
         # new sample to its cluster and re-optimise from the previous theta instead of refitting from scratch
         self.INCREMENTAL = g("INCREMENTAL_CGP", False)
-        # exact bound-pruned EI scan (cgp_ei_argmax_pruned): same selected sample, several times faster acquisition
-        self.PRUNED_SCAN = g("PRUNED_SCAN_CGP", False)
+        # exact bound-pruned EI scan (cgp_ei_argmax_pruned, default): same selected sample, several times faster acquisition;
+        # False = score every candidate
+        self.PRUNED_SCAN = g("PRUNED_SCAN_CGP", True)
         self.PILOT_SAMPLES = g("PILOT_SAMPLES_CGP", None)
         self.OUTPUT_NAME = g("OUTPUT_NAME_CGP", None)
         self.OBJ_NAME = g("OBJ_NAME_CGP", None)
@@ -260,7 +261,8 @@ def main(argv=None):
     p.add_option("--candidates", type="int", dest="CANDIDATES", default=65536)
     p.add_option("--restarts", type="int", dest="RESTARTS", default=None)
     p.add_option("--incremental", action="store_true", dest="INCREMENTAL", default=False)
-    p.add_option("--pruned-scan", action="store_true", dest="PRUNED", default=False)
+    p.add_option("--pruned-scan", action="store_true", dest="PRUNED", default=True)
+    p.add_option("--exhaustive-scan", action="store_false", dest="PRUNED")
     o, _ = p.parse_args(argv)
     if o.N_SEQUENTIAL is None:
         raise Exception("ERROR: N_SEQEUNTIAL(int) is a compulsory parameter that must be supplied. \n e.g. -s 20")

@@ -180,7 +180,7 @@ class ClusterGPEngine:
         return self.lml_grad_collect(self.lml_grad_submit(pair_cluster, thetas, want_grad))
 
     # ------------------------------------------------------------------ fit
-    def fit(self, n_restarts, seed=0, theta0=None, bounds=None, optimize=True, shard_mode=None):
+    def fit(self, n_restarts, seed=0, theta0=None, bounds=None, optimize=True, shard_mode=None, max_lockstep=None):
         """All clusters x (R+1) restarts in lock-step (SK/_gpr.py:296-340), sharded over ranks, then the final
         factorisation at each cluster's best theta (SK/_gpr.py:349-367).
 
@@ -189,7 +189,9 @@ class ClusterGPEngine:
         even although run lengths range from 2 to 167 evaluations.  "static": the (cluster, restart) pairs are dealt
         round-robin once, each rank optimises its own pairs, one all-gather of (theta*, -lml) rows follows.
         Measured on 8 B200, config 3: balanced 2.62 s / iteration, static 2.70 s (its slowest rank draws 754 of the 4938
-        evaluations, mean 617).  Both select the same point with the same score bits."""
+        evaluations, mean 617).  Both select the same point with the same score bits.
+        max_lockstep: cut the optimisation after that many lock-steps (each run keeps its best evaluated theta): the
+        single-65536-sample-cluster configuration measures ONE lock-step of its R+1 runs (9 s per evaluation)."""
         if shard_mode is None:
             shard_mode = os.environ.get("CGP_SHARD_MODE", "balanced")
         rank, ws = cdist.world()
@@ -252,7 +254,8 @@ class ClusterGPEngine:
         try:
             xs, fs, nfev, nit, steps = minimize_lockstep(eval_batch, x0s, lo, hi, submit=submit, collect=collect,
                                                          pipeline_min=int(os.environ.get("CGP_PIPELINE_MIN", "256")),
-                                                         shard=shard)
+                                                         shard=shard, **({} if max_lockstep is None else
+                                                                         {"max_steps": int(max_lockstep)}))
         finally:
             if gc_was_on:
                 gc.enable()
@@ -524,12 +527,14 @@ class ClusterGPEngine:
             arr[perm] = -neg_sorted
         return (-best[0], best[1], best[2]), arr
 
-    def select_next(self, candidates, k=3, sharded=False, prune=False):
+    def select_next(self, candidates, k=3, sharded=False, prune=True):
         """Pick the next sample from `candidates` [M,d].
 
         sharded=False: `candidates` is the full array (identical on every rank); each rank scores its
         contiguous shard.  sharded=True: `candidates` is already this rank's shard and idx_base is derived
-        from the shard sizes (all-gathered).  Returns (x_next np[d], score, global idx, cluster)."""
+        from the shard sizes (all-gathered).  Returns (x_next np[d], score, global idx, cluster).
+        prune=True (default): the exact bound-pruned scan (cgp_ei_argmax_pruned) — same selected candidate and the same
+        score bits as the exhaustive scan (tests/test_gpu_prune.py); prune=False scores every candidate."""
         rank, ws = cdist.world()
         if sharded:
             local = self._to_dev(candidates)

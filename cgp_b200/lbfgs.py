@@ -43,7 +43,7 @@ class _Run:
     """One L-BFGS-B state machine (the body of _minimize_lbfgsb's while-loop, turned inside out)."""
 
     __slots__ = ("x", "f", "g", "lo", "hi", "nbd", "wa", "iwa", "task", "ln_task", "lsave", "isave", "dsave", "m",
-                 "factr", "pgtol", "maxls", "maxiter", "maxfun", "nit", "nfev", "done")
+                 "factr", "pgtol", "maxls", "maxiter", "maxfun", "nit", "nfev", "done", "best_f", "best_x")
 
     def __init__(self, x0, lo, hi, m=10, ftol=2.2204460492503131e-09, gtol=1e-5, maxfun=15000, maxiter=15000,
                  maxls=20):
@@ -70,6 +70,8 @@ class _Run:
         self.nit = 0
         self.nfev = 0
         self.done = False
+        self.best_f = np.inf   # best evaluated point so far: the result of a run cut off by max_steps
+        self.best_x = self.x.copy()
 
     def advance(self):
         """Run setulb until it asks for (f, g) at self.x (returns True) or terminates (returns False)."""
@@ -95,6 +97,8 @@ class _Run:
         self.f = float(f)
         self.g = np.array(g, dtype=np.float64)
         self.nfev += 1
+        if self.f < self.best_f:
+            self.best_f, self.best_x = self.f, self.x.copy()
 
 
 def minimize_lockstep(eval_batch, x0s, lo, hi, max_steps=100000, submit=None, collect=None, pipeline_min=256,
@@ -109,6 +113,7 @@ def minimize_lockstep(eval_batch, x0s, lo, hi, max_steps=100000, submit=None, co
     lock-step the waiting runs are dealt to the ranks (heaviest first, round-robin), each rank evaluates only its share
     and ``allreduce`` (sum over ranks of a [b, n+1] array whose foreign rows are zero) hands every rank all (f, g).
     The machines then advance identically everywhere, so the work stays balanced as runs finish at different times.
+    max_steps: stop after that many lock-steps; unfinished runs return their best evaluated point.
     Returns (x [R, n], f [R], nfev [R], nit [R], n_lockstep)."""
     runs = [_Run(np.asarray(x0), lo, hi) for x0 in x0s]
     waiting = [i for i, r in enumerate(runs) if r.advance()]
@@ -166,6 +171,7 @@ def minimize_lockstep(eval_batch, x0s, lo, hi, max_steps=100000, submit=None, co
             f, g = eval_batch(idx, X)
         waiting = absorb(waiting, f, g)
         steps += 1
-    xs = np.stack([r.x for r in runs])
-    fs = np.array([float(r.f) for r in runs])
+    # finished runs: SciPy's result (x, f of the last accepted iterate); runs cut off by max_steps: best evaluated point
+    xs = np.stack([r.x if r.done else r.best_x for r in runs])
+    fs = np.array([float(r.f) if r.done else float(r.best_f) for r in runs])
     return xs, fs, np.array([r.nfev for r in runs]), np.array([r.nit for r in runs]), steps

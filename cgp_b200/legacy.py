@@ -62,21 +62,42 @@ def extract_arrays(obj):
     return dict(gprs=gprs, classify=clf)
 
 
-def load_reference_model(path):
-    """-> {'Cluster', 'Classify', 'GPR_list'} with B200-backed objects (needs a CUDA device for GPR_list / predict)."""
-    from .gpr import GaussianProcessRegressor, KNeighborsClassifier, parse_kernel
+def model_from_arrays(arr, cluster=None):
+    """B200-backed {'Cluster', 'Classify', 'GPR_list'} from the plain arrays of extract_arrays (needs a CUDA device).
+    A GPR entry needs X, y_norm, y_mean, y_std, theta, alpha and either ``kernel`` (the fitted sklearn kernel object)
+    or ``kind`` ("matern32" | "rbf": the reference's template REF/cGP/cGP_constrained.py:169 is rebuilt)."""
+    from .gpr import GaussianProcessRegressor, KNeighborsClassifier
 
-    obj = _permissive_load(path)
-    arr = extract_arrays(obj)
-    out = {"Cluster": obj.get("Cluster"), "GPR_list": []}
+    out = {"Cluster": cluster, "GPR_list": []}
     out["Classify"] = KNeighborsClassifier(arr["classify"]["k"]).fit(arr["classify"]["X"], arr["classify"]["labels"])
     for a in arr["gprs"]:
         if a is None:
             out["GPR_list"].append(None)
             continue
-        kind, _, _, _ = parse_kernel(a["kernel"], a["X"].shape[1])
-        kern = a["kernel"].clone_with_theta(a["theta"])
+        kern = a.get("kernel")
+        if kern is None:
+            from sklearn.gaussian_process.kernels import RBF, Matern, WhiteKernel
+
+            d = a["X"].shape[1]
+            base = Matern(length_scale=np.ones(d), length_scale_bounds=(1e-05, 100000.0), nu=1.5) \
+                if a.get("kind", "matern32") == "matern32" else RBF(length_scale=np.ones(d), length_scale_bounds=(1e-05, 100000.0))
+            kern = base + WhiteKernel(noise_level=1.0, noise_level_bounds=(1e-05, 100000.0))
+        kern = kern.clone_with_theta(a["theta"])
         g = GaussianProcessRegressor(kernel=kern, alpha=a["alpha"], normalize_y=True, optimizer=None, random_state=0)
         g.fit(a["X"], (a["y_norm"] * a["y_std"] + a["y_mean"]).reshape(-1, 1))  # one factorisation at the stored theta
         out["GPR_list"].append(g)
     return out
+
+
+def load_reference_model(path):
+    """-> {'Cluster', 'Classify', 'GPR_list'} with B200-backed objects (needs a CUDA device for GPR_list / predict)."""
+    obj = _permissive_load(path)
+    return model_from_arrays(extract_arrays(obj), obj.get("Cluster"))
+
+
+def f_truth(model, X):
+    """REF/cGP/f_truth_dill.py:20-30: route one point with the k-NN classifier, return that cluster's posterior mean."""
+    x = np.asarray(X, dtype=np.float64).reshape(1, -1)
+    lab = int(model["Classify"].predict(x)[0])
+    mu = model["GPR_list"][lab].predict(x, return_std=True, return_cov=False)[0]
+    return float(np.asarray(mu).reshape(-1)[0])

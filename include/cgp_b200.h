@@ -178,6 +178,11 @@ int cgp_profile_classes(void);
 const char* cgp_profile_class_name(int cls);
 int cgp_profile_enable(cgp_handle* h, int on);
 int cgp_profile_read(cgp_handle* h, double* ms, int64_t* launches, int n_cls, int reset);
+/* Algorithmic flops (real rows / columns only) and count of the TIMED launches per class since the last
+ * reset; call before the resetting cgp_profile_read().  Batches of at most CGP_FORK_MAX (default 24) matrices run the
+ * three-stream look-ahead schedule: their launches are counted but never timed (a bracket there would include work of
+ * the other two streams); larger batches run on one stream, so ms / flops describe exclusive kernel time. */
+int cgp_profile_flops(cgp_handle* h, double* flops, int64_t* timed, int n_cls);
 
 #ifdef __cplusplus
 }

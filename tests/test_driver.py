@@ -56,9 +56,9 @@ def test_driver_cli_end_to_end(tmp_path, monkeypatch):
     X, Y = driver.main(["-p", "20", "-s", "3", "-C", "KMeans2", "-N", "classify", "-f", "cgp_b200.plugins.f_bukin",
                         "-r", "123", "-o", "bukin_run", "-d", "bukin_model", "-X", "--candidates", "4096", "--restarts", "2"])
     assert X.shape == (23, 2) and Y.shape == (23, 1)
-    # the exact pruned scan walks the same trajectory (same seed -> same candidates -> same selections)
+    # the exhaustive scan walks the same trajectory as the (default) exact pruned scan (same seed -> same candidates -> same selections)
     Xp, Yp = driver.main(["-p", "20", "-s", "3", "-C", "KMeans2", "-N", "classify", "-f", "cgp_b200.plugins.f_bukin",
-                          "-r", "123", "-o", "bukin_run_p", "-X", "--candidates", "4096", "--restarts", "2", "--pruned-scan"])
+                          "-r", "123", "-o", "bukin_run_p", "-X", "--candidates", "4096", "--restarts", "2", "--exhaustive-scan"])
     assert np.array_equal(X, Xp) and np.array_equal(Y, Yp)
     assert os.path.exists("bukin_run.txt") and os.path.exists("bukin_run.log") and os.path.exists("bukin_model.pkl")
     with open("bukin_model.pkl", "rb") as f:

@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 import oracle
-from conftest import relerr
+from conftest import relerr, var_excess
 
 pytestmark = pytest.mark.gpu
 
@@ -55,8 +55,7 @@ def test_append_equals_refactorisation_and_oracle(kind):
     (bs, bi, bc), (sc, mu, sd) = eng.ei_scan(Q, 3, want_arrays=True)
     (rs, ri, rc), (rsc, rmu, rsd) = ref.ei_scan(Q, 3, want_arrays=True)
     assert relerr(mu.cpu().numpy(), rmu.cpu().numpy()) < 1e-8
-    ok = rsd.cpu().numpy() > 1e-3
-    assert relerr(sd.cpu().numpy()[ok], rsd.cpu().numpy()[ok]) < 1e-7
+    assert var_excess(sd.cpu().numpy(), rsd.cpu().numpy()) <= 1.0
     assert int(bi.item()) == int(ri.item()) and int(bc.item()) == int(rc.item())
 
 

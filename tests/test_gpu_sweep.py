@@ -5,7 +5,7 @@ import pytest
 import torch
 
 import oracle
-from conftest import relerr
+from conftest import relerr, var_excess
 
 pytestmark = pytest.mark.gpu
 
@@ -47,8 +47,7 @@ def test_lml_grad_predict_sweep(d, kind):
     (bs, bi, bc), (score, mean, std) = eng.ei_scan(Q, 3, want_arrays=True)
     assert np.array_equal(eng.route(Q, 3).cpu().numpy(), ref["labels"])
     assert relerr(mean.cpu().numpy(), ref["mean"]) < 1e-7
-    ok = ref["std"] > 1e-3
-    assert relerr(std.cpu().numpy()[ok], ref["std"][ok]) < 1e-6
+    assert var_excess(std.cpu().numpy(), ref["std"]) <= 1.0
     assert int(bi.item()) == ref["best_idx"]
 
 

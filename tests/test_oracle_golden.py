@@ -87,3 +87,50 @@ def test_merge_and_recode():
     assert set(np.unique(m)) == {1, 3}
     r = oracle.recode(m)
     assert set(np.unique(r)) == {0, 1} and r[0] == 1 and r[-1] == 0
+
+
+def test_oracle_at_config5_shape_and_extended_truth():
+    """cfg5-shaped golden (n_c = 480 / 512 / 544, 8-D): the oracle restatement against scikit-learn at the north-star
+    tolerance, and both against the long-double truth (oracle/extended.py) — variance included, down to 3e-5 of the
+    prior.  One cluster here (CPU budget); the GPU suite covers all three."""
+    from oracle import extended as E
+
+    g = load_golden("cfg5_shape")
+    X, y, lab, Q = g["X"], g["y"], g["labels"].astype(np.int64), g["Q"]
+    ql = g["qlab"].astype(np.int64)
+    assert np.array_equal(oracle.knn_labels(X, lab, Q[:1500], k=3), ql[:1500])
+    c = 1
+    Xt, yt, th = X[lab == c], y[lab == c], g[f"c{c}_theta"]
+    yn, ym, ys = oracle.normalize_y(yt)
+    lml, grad = oracle.lml_and_grad(Xt, yn, th, 1e-5)
+    assert abs(lml - g[f"c{c}_lml"][0]) <= RTOL * abs(lml)
+    assert np.max(np.abs(grad - g[f"c{c}_grad"])) <= 1e-7 * max(1.0, abs(lml) * 1e-3)
+    K = oracle.kernel_matrix(Xt, th, "matern32", 1e-5)
+    L = np.linalg.cholesky(K)
+    ti = g["truth_idx"][ql[g["truth_idx"]] == c][:300]
+    mu, sd = oracle.predict_mean_std(Xt, th, L, np.linalg.solve(K, yn), ym, ys, Q[ti])
+    assert relerr(mu, g["mean"][ti]) < RTOL
+    assert relerr(sd ** 2, g["std"][ti] ** 2) < RTOL  # variance, no floor
+    # long-double truth recomputed here == the committed one; sklearn and the oracle are both within 1e-8 of it
+    pos = np.nonzero(np.isin(g["truth_idx"], ti))[0]
+    truth = np.asarray(E.predict_var_truth(Xt, th, Q[ti]), dtype=np.float64)
+    assert relerr(truth, g["truth_var_norm"][pos]) < 1e-12
+    assert relerr((g["std"][ti] / ys) ** 2, truth) < RTOL and relerr((sd / ys) ** 2, truth) < RTOL
+    assert abs(float(E.lml_truth(Xt, yn, th)) - lml) <= 1e-10 * abs(lml)
+
+
+def test_config2_golden_is_consistent():
+    """cfg2_full golden: data regenerated from seeds (tools/workloads.py) + stored DGM4 labels; oracle LML at scikit-learn's
+    theta and k-NN labels on a subset."""
+    from tools import workloads as W
+
+    g = load_golden("cfg2_full")
+    X, y = W.cfg2_samples()
+    lab = g["labels"].astype(np.int64)
+    assert X.shape == (2000, 2) and lab.shape == (2000,)
+    Q = W.cfg2_candidates()
+    assert np.array_equal(oracle.knn_labels(X, lab, Q[:2000], k=3), g["qlab"][:2000].astype(np.int64))
+    c = int(np.argmin(np.bincount(lab)))
+    yn, _, _ = oracle.normalize_y(y[lab == c])
+    lml = oracle.lml_and_grad(X[lab == c], yn, g[f"c{c}_theta"], 1e-5, want_grad=False)
+    assert abs(lml - g[f"c{c}_lml"][0]) <= RTOL * abs(lml)
