@@ -40,9 +40,9 @@ SIGNATURES = {
     "cgp_predict": (C.c_int, [_vp, C.c_int, _vp, _pi64, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64,
                               _vp, _vp, _vp, _sz, _vp]),
     "cgp_ei_argmax": (C.c_int, [_vp, C.c_int, _vp, _pi64, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
-                                _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+                                _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "cgp_ei_argmax_pruned": (C.c_int, [_vp, C.c_int, _vp, _pi64, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
-                                       _i64, _i64, _vp, _vp, _vp, _vp, _sz, _vp]),
+                                       _i64, _i64, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "cgp_append_workspace_bytes": (_sz, [_i64]),
     "cgp_append_sample": (C.c_int, [_vp, C.c_int, _vp, _i64, C.c_int, _vp, _f64, _vp, _vp, _i64, _vp, _vp, _sz, _vp]),
     "cgp_refresh_alpha": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _sz, _vp]),
@@ -54,6 +54,9 @@ SIGNATURES = {
     "cgp_profile_enable": (C.c_int, [_vp, C.c_int]),
     "cgp_profile_read": (C.c_int, [_vp, C.POINTER(C.c_double), _pi64, C.c_int, C.c_int]),
     "cgp_profile_flops": (C.c_int, [_vp, C.POINTER(C.c_double), _pi64, C.c_int]),
+    "cgp_profile_mute": (C.c_int, [_vp, C.c_int]),
+    "cgp_set_option": (C.c_int, [_vp, C.c_int, C.c_int]),
+    "cgp_get_option": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_int)]),
 }
 
 _lib = None
@@ -80,16 +83,25 @@ def lib():
     return _lib
 
 
-def handle(device=None):
+def handle(device=None, lane=0):
+    """The library handle of (device, lane).  Lane 0 is the default; further lanes are independent handles (their own
+    internal streams, events and metadata ring) for batches that run CONCURRENTLY on the same device (engine.fit)."""
     if not torch.cuda.is_available():
         raise CgpError("cgp_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
     dev = torch.cuda.current_device() if device is None else int(device)
-    if dev not in _handles:
+    key = dev if lane == 0 else (dev, int(lane))
+    if key not in _handles:
         h = _vp()
         with torch.cuda.device(dev):
             _chk(lib().cgp_create(C.byref(h), dev), "cgp_create")
-        _handles[dev] = h
-    return _handles[dev]
+        _handles[key] = h
+    return _handles[key]
+
+
+def lanes_of(device=None):
+    """Lane ids of the handles that exist on `device`."""
+    dev = torch.cuda.current_device() if device is None else int(device)
+    return [0 if k == dev else k[1] for k in _handles if k == dev or (isinstance(k, tuple) and k[0] == dev)]
 
 
 def _chk(rc, what):
@@ -164,7 +176,7 @@ def lml_workspace_bytes(offs, pair_cluster, d):
     return int(lib().cgp_lml_workspace_bytes(po, len(o) - 1, ppc, len(pc), d))
 
 
-def lml_grad_batched(X, y, offs, pair_cluster, theta, alpha, kind, workspace, want_grad=True, out=None):
+def lml_grad_batched(X, y, offs, pair_cluster, theta, alpha, kind, workspace, want_grad=True, out=None, lane=0):
     """theta [B,P] CUDA -> (lml [B], grad [B,P] | None, info [B]) CUDA tensors (asynchronous).
     `out` = (lml, grad, info) preallocated contiguous CUDA tensors of exactly these shapes (no allocation then)."""
     o, po = _host_i64(offs)
@@ -181,7 +193,7 @@ def lml_grad_batched(X, y, offs, pair_cluster, theta, alpha, kind, workspace, wa
         lml = torch.empty(B, dtype=torch.float64, device=X.device)
         grad = torch.empty((B, P), dtype=torch.float64, device=X.device) if want_grad else None
         info = torch.empty(B, dtype=torch.int32, device=X.device)
-    _chk(lib().cgp_lml_grad_batched(handle(X.device.index), KIND[kind], _ptr(X), _ptr(y), po, len(o) - 1, d, ppc, B,
+    _chk(lib().cgp_lml_grad_batched(handle(X.device.index, lane), KIND[kind], _ptr(X), _ptr(y), po, len(o) - 1, d, ppc, B,
                                     _ptr(theta), float(alpha), _ptr(lml), _ptr(grad), _ptr(info, torch.int32),
                                     _ptr(workspace, torch.uint8), workspace.numel(), _stream(X.device)),
          "cgp_lml_grad_batched")
@@ -295,9 +307,12 @@ def predict(X, offs, theta, W, alpha_vec, y_mean, y_std, Q, qlabel, kind, want_s
 
 
 def ei_argmax(X, offs, theta, W, alpha_vec, y_mean, y_std, y_max, Q, qlabel, kind, idx_base=0, want_arrays=False,
-              workspace=None, prune=False):
+              workspace=None, prune=False, penalty=None):
     """-> (best [score f64, idx i64, cluster i64] as CUDA tensors, score/mean/std arrays or None).
-    prune=True: exact bound-pruned scan (cgp_ei_argmax_pruned): same selection, no per-candidate arrays."""
+    prune=True: exact bound-pruned scan (cgp_ei_argmax_pruned): same selection, no per-candidate arrays.
+    penalty: [m] CUDA f64 additive soft-constraint term (score = (EI + penalty) / n_c) or None."""
+    if penalty is not None and penalty.shape != (Q.shape[0],):
+        raise CgpError("penalty must have one entry per candidate")
     o, po = _host_i64(offs)
     d = X.shape[1]
     m = Q.shape[0]
@@ -317,22 +332,46 @@ def ei_argmax(X, offs, theta, W, alpha_vec, y_mean, y_std, y_max, Q, qlabel, kin
             raise CgpError("the pruned scan has no per-candidate outputs (pruned candidates are never scored exactly)")
         _chk(lib().cgp_ei_argmax_pruned(handle(dev.index), KIND[kind], _ptr(X), po, len(o) - 1, d, _ptr(theta), _ptr(W),
                                         _ptr(alpha_vec), _ptr(y_mean), _ptr(y_std), _ptr(y_max), _ptr(Q),
-                                        _ptr(qlabel, torch.int64), m, int(idx_base), _ptr(bs), _ptr(bi, torch.int64),
-                                        _ptr(bc, torch.int64), _ptr(workspace, torch.uint8), workspace.numel(),
+                                        _ptr(qlabel, torch.int64), m, int(idx_base), _ptr(penalty), _ptr(bs),
+                                        _ptr(bi, torch.int64), _ptr(bc, torch.int64), _ptr(workspace, torch.uint8),
+                                        workspace.numel(),
                                         _stream(dev)), "cgp_ei_argmax_pruned")
         return (bs, bi, bc), (None, None, None)
     _chk(lib().cgp_ei_argmax(handle(dev.index), KIND[kind], _ptr(X), po, len(o) - 1, d, _ptr(theta), _ptr(W),
                              _ptr(alpha_vec), _ptr(y_mean), _ptr(y_std), _ptr(y_max), _ptr(Q),
-                             _ptr(qlabel, torch.int64), m, int(idx_base), _ptr(score), _ptr(mean), _ptr(std),
+                             _ptr(qlabel, torch.int64), m, int(idx_base), _ptr(penalty), _ptr(score), _ptr(mean), _ptr(std),
                              _ptr(bs), _ptr(bi, torch.int64), _ptr(bc, torch.int64), _ptr(workspace, torch.uint8),
                              workspace.numel(), _stream(dev)), "cgp_ei_argmax")
     return (bs, bi, bc), (score, mean, std)
 
 
+OPTIONS = {"knn_mode": 1, "fork_max": 2, "tile_mode": 3}
+KNN_MODES = {"auto": 0, "exact": 1, "tc": 2}
+
+
+def set_option(name, value, device=None):
+    """Runtime switch on every lane handle of `device` (include/cgp_b200.h: cgp_set_option).  Returns the old value."""
+    if name == "knn_mode" and isinstance(value, str):
+        value = KNN_MODES[value]
+    old = C.c_int()
+    _chk(lib().cgp_get_option(handle(device), OPTIONS[name], C.byref(old)), "cgp_get_option")
+    for lane in lanes_of(device):
+        _chk(lib().cgp_set_option(handle(device, lane), OPTIONS[name], int(value)), "cgp_set_option")
+    return old.value
+
+
 # ------------------------------------------------------------------------------------------------ measurement
 def profile_enable(on=True, device=None):
-    """on: False/0 off, True/1 every launch timed, 2 only the large kernels (see include/cgp_b200.h)."""
-    _chk(lib().cgp_profile_enable(handle(device), int(on)), "cgp_profile_enable")
+    """on: False/0 off, True/1 every launch timed, 2 only the large kernels (see include/cgp_b200.h).  All lanes."""
+    handle(device)
+    for lane in lanes_of(device):
+        _chk(lib().cgp_profile_enable(handle(device, lane), int(on)), "cgp_profile_enable")
+
+
+def profile_mute(on, device=None, lane=0):
+    """Count but do not time the following launches of this lane (set while another lane runs concurrently: an event
+    bracket would then include the other lane's work)."""
+    _chk(lib().cgp_profile_mute(handle(device, lane), 1 if on else 0), "cgp_profile_mute")
 
 
 def profile_read(reset=True, device=None, detail=False):
@@ -341,14 +380,19 @@ def profile_read(reset=True, device=None, detail=False):
     events (exclusive kernel time: batches on the three-stream schedule are counted in `launches` but not timed)."""
     L = lib()
     n = L.cgp_profile_classes()
-    ms = (C.c_double * n)()
-    cnt = (C.c_int64 * n)()
-    fl = (C.c_double * n)()
-    timed = (C.c_int64 * n)()
-    if detail:
-        _chk(L.cgp_profile_flops(handle(device), fl, timed, n), "cgp_profile_flops")
-    _chk(L.cgp_profile_read(handle(device), ms, cnt, n, 1 if reset else 0), "cgp_profile_read")
     names = [L.cgp_profile_class_name(i).decode() for i in range(n)]
+    tot = {nm: dict(ms=0.0, launches=0, timed=0, flops=0.0) for nm in names}
+    handle(device)
+    for lane in lanes_of(device):  # totals over all lanes of the device
+        ms = (C.c_double * n)()
+        cnt = (C.c_int64 * n)()
+        fl = (C.c_double * n)()
+        timed = (C.c_int64 * n)()
+        _chk(L.cgp_profile_flops(handle(device, lane), fl, timed, n), "cgp_profile_flops")
+        _chk(L.cgp_profile_read(handle(device, lane), ms, cnt, n, 1 if reset else 0), "cgp_profile_read")
+        for i, nm in enumerate(names):
+            t = tot[nm]
+            t["ms"] += float(ms[i]); t["launches"] += int(cnt[i]); t["timed"] += int(timed[i]); t["flops"] += float(fl[i])
     if detail:
-        return {names[i]: dict(ms=float(ms[i]), launches=int(cnt[i]), timed=int(timed[i]), flops=float(fl[i])) for i in range(n)}
-    return {names[i]: (float(ms[i]), int(cnt[i])) for i in range(n)}
+        return tot
+    return {nm: (t["ms"], t["launches"]) for nm, t in tot.items()}

@@ -91,11 +91,12 @@ class CGPRegressor:
         return dict(labels=ql.cpu().numpy(), mean=mean.cpu().numpy(), std=std.cpu().numpy(), score=score.cpu().numpy(),
                     best_score=float(bs.item()), best_idx=int(bi.item()), best_cluster=int(bc.item()))
 
-    def select_next(self, candidates, sharded=False, prune=True):
+    def select_next(self, candidates, sharded=False, prune=True, boundary_penalty=None):
         """-> (x_next [d], score, idx).  Multi-GPU aware (see cgp_b200/dist.py).  prune=True (default): exact bound-pruned
         scan, same selection and score bits (candidates whose EI bound from the predictive mean cannot reach the running
         best skip the variance contraction); prune=False: exhaustive scan."""
-        x, score, idx, _cl = self.engine_.select_next(candidates, self.n_neighbors, sharded=sharded, prune=prune)
+        x, score, idx, _cl = self.engine_.select_next(candidates, self.n_neighbors, sharded=sharded, prune=prune,
+                                                      boundary_penalty=boundary_penalty)
         return x, score, idx
 
     def select_next_mspe(self, candidates):

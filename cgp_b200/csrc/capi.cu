@@ -14,6 +14,7 @@
 #include "gemm_nt.cuh"
 #include "kernel_fn.cuh"
 #include "knn.cuh"
+#include "knn_tc.cuh"
 #include "score.cuh"
 
 #define CGP_VERSION 100
@@ -26,13 +27,13 @@ enum {
     CLS_ASSEMBLE, CLS_POTRF_UPDATE, CLS_POTRF_TRAIL, CLS_POTRF_DIAG, CLS_POTRF_PANEL, CLS_TRTRI_ACC, CLS_TRTRI_TRAIL,
     CLS_TRTRI_SCALE, CLS_SOLVE,
     CLS_LAUUM, CLS_GRAD, CLS_TRANSPOSE, CLS_KNN, CLS_BUCKET, CLS_CROSS, CLS_MEAN, CLS_PREDICT_VNORM,
-    CLS_SCORE_FINISH, CLS_ARGMAX, CLS_DGEMM, CLS_APPEND, CLS_COUNT
+    CLS_SCORE_FINISH, CLS_ARGMAX, CLS_DGEMM, CLS_APPEND, CLS_KNN_PREP, CLS_KNN_EXACT, CLS_COUNT
 };
 static const char* const kClassNames[CLS_COUNT] = {
     "assemble", "potrf_update", "potrf_trail", "potrf_diag", "potrf_panel", "trtri_acc", "trtri_trail",
     "trtri_scale", "solve_lml",
     "lauum", "grad", "transpose", "knn", "bucket", "cross", "mean", "predict_vnorm",
-    "score_finish", "argmax", "dgemm_nt", "append"};
+    "score_finish", "argmax", "dgemm_nt", "append", "knn_prep", "knn_exact"};
 
 struct ProfRec {
     cudaEvent_t a, b;
@@ -46,6 +47,7 @@ struct HandleImpl : cgp_handle {
     // per-kernel-class launch counters (always) and CUDA-event timing (when enabled)
     int prof_on;      // 0 off, 1 every launch bracketed by events, 2 only the large kernels the roofline is quoted for
     bool prof_skip;   // the launch in flight is counted but not timed
+    bool user_mute;   // cgp_profile_mute: another lane (handle) runs concurrently on this device -> count only
     bool prof_mute;   // inside a forked (three-stream) batch: brackets would overlap other streams -> count only
     std::vector<ProfRec> recs;
     size_t recs_used;
@@ -54,6 +56,9 @@ struct HandleImpl : cgp_handle {
     double pending_flops;          // set by FL() for the next KL launch
     long long launches[CLS_COUNT];
     long long timed[CLS_COUNT];    // launches that were bracketed by events
+    void* knn_buf;     // scratch of the tensor-core k-NN prefilter (grow-only)
+    size_t knn_bytes;
+    int knn_mode;      // 0 = by problem size, 1 = always the exact fp64 kernel, 2 = prefilter whenever k <= 3 (CGP_KNN_MODE)
     int fork_max;  // batches with more matrices than this run the one-stream schedule (CGP_FORK_MAX, default 24)
     // internal streams of run_pipeline: sc (high priority) = the dependent chain update -> diag -> panel + look-ahead part
     // of the trailing update; s2 (low priority) = triangular-inverse work of panel p beside the Cholesky of panel p+1.
@@ -66,14 +71,14 @@ struct HandleImpl : cgp_handle {
 
 static inline void prof_begin(HandleImpl* h, int cls, cudaStream_t s) {
     h->launches[cls]++;
-    if (!h->prof_on || h->prof_mute) {
+    if (!h->prof_on || h->prof_mute || h->user_mute) {
         h->prof_skip = true;
         return;
     }
     // level 2: the event pair costs ~2 x 1.5 us of stream latency per launch, which is visible on the latency-bound
     // chain of small kernels (diag / panel / update ...) when few matrices are in flight; time only the big ones.
     h->prof_skip = h->prof_on == 2 && !(cls == CLS_LAUUM || cls == CLS_PREDICT_VNORM || cls == CLS_POTRF_TRAIL ||
-                                        cls == CLS_TRTRI_TRAIL || cls == CLS_KNN || cls == CLS_CROSS || cls == CLS_GRAD ||
+                                        cls == CLS_TRTRI_TRAIL || cls == CLS_KNN || cls == CLS_KNN_EXACT || cls == CLS_CROSS || cls == CLS_GRAD ||
                                         cls == CLS_ASSEMBLE);
     if (h->prof_skip) return;
     if (h->recs_used == h->recs.size()) {
@@ -149,6 +154,7 @@ static void handle_free(HandleImpl* h) {
     if (h->s2) cudaStreamDestroy(h->s2);
     if (h->sc) cudaStreamDestroy(h->sc);
     if (h->pinned) cudaFreeHost(h->pinned);
+    if (h->knn_buf) cudaFree(h->knn_buf);
     delete h;
 }
 
@@ -215,6 +221,13 @@ extern "C" int cgp_create(cgp_handle** out, int device) {
     for (int i = 0; i < CLS_COUNT; ++i) h->ms[i] = 0.0, h->launches[i] = 0, h->flops[i] = 0.0, h->timed[i] = 0;
     h->pending_flops = 0.0;
     h->prof_mute = false;
+    h->user_mute = false;
+    h->knn_buf = nullptr;
+    h->knn_bytes = 0;
+    {
+        const char* e = getenv("CGP_KNN_MODE");
+        h->knn_mode = (e && !strcmp(e, "exact")) ? 1 : (e && !strcmp(e, "tc")) ? 2 : 0;
+    }
     {
         const char* e = getenv("CGP_FORK_MAX");
         h->fork_max = e ? atoi(e) : 24;
@@ -236,11 +249,52 @@ extern "C" int cgp_destroy(cgp_handle* hh) {
     return 0;
 }
 
+// Runtime switches (the environment variables of the same name set the defaults at cgp_create):
+//   CGP_OPT_KNN_MODE 0 by size | 1 exact fp64 kernel only | 2 tensor-core prefilter whenever k <= 3
+//   CGP_OPT_FORK_MAX batches with more matrices than this use the one-stream schedule (0 = never fork)
+//   CGP_OPT_TILE_MODE 0 by launch size | 1 always 128x128 CTAs | 2 always the small shapes
+extern "C" int cgp_set_option(cgp_handle* hh, int option, int value) {
+    if (!hh) return -1;
+    HandleImpl* h = static_cast<HandleImpl*>(hh);
+    switch (option) {
+        case CGP_OPT_KNN_MODE:
+            if (value < 0 || value > 2) return -3;
+            h->knn_mode = value;
+            return 0;
+        case CGP_OPT_FORK_MAX:
+            if (value < 0) return -3;
+            h->fork_max = value;
+            return 0;
+        case CGP_OPT_TILE_MODE:
+            if (value < 0 || value > 2) return -3;
+            h->tile_mode = value;
+            return 0;
+    }
+    return -2;
+}
+extern "C" int cgp_get_option(cgp_handle* hh, int option, int* value) {
+    if (!hh) return -1;
+    if (!value) return -3;
+    HandleImpl* h = static_cast<HandleImpl*>(hh);
+    switch (option) {
+        case CGP_OPT_KNN_MODE: *value = h->knn_mode; return 0;
+        case CGP_OPT_FORK_MAX: *value = h->fork_max; return 0;
+        case CGP_OPT_TILE_MODE: *value = h->tile_mode; return 0;
+    }
+    return -2;
+}
+
 extern "C" int cgp_profile_classes(void) { return CLS_COUNT; }
 extern "C" const char* cgp_profile_class_name(int cls) { return (cls >= 0 && cls < CLS_COUNT) ? kClassNames[cls] : ""; }
 extern "C" int cgp_profile_enable(cgp_handle* hh, int on) {
     if (!hh) return -1;
     static_cast<HandleImpl*>(hh)->prof_on = on < 0 ? 0 : (on > 2 ? 2 : on);
+    return 0;
+}
+// Count but do not time the following launches (the caller runs another handle's batch concurrently on this device).
+extern "C" int cgp_profile_mute(cgp_handle* hh, int on) {
+    if (!hh) return -1;
+    static_cast<HandleImpl*>(hh)->user_mute = on != 0;
     return 0;
 }
 // Folds the finished event pairs into ms[] (synchronises on them), copies the totals out and optionally resets.
@@ -802,6 +856,35 @@ extern "C" int cgp_refresh_alpha(cgp_handle* hh, const double* L, const double* 
 // ------------------------------------------------------------------------------------------------
 // k-NN routing
 // ------------------------------------------------------------------------------------------------
+// Tensor-core prefilter (knn_tc.cuh) in front of the exact kernel: worth it for large training sets and many queries.
+// CGP_KNN_MODE = "exact" | "tc" forces one path (tests run both).
+template <int DP>
+static int launch_knn_tc(HandleImpl* h, const double* X, const long long* lab, int n, int d, int k, const double* Q, long long M,
+                         long long* out, cudaStream_t s) {
+    const int npad = (n + KTC_TILE - 1) / KTC_TILE * KTC_TILE;
+    const size_t o_xn = align_up((size_t)npad * DP * 8, 256), o_st = align_up(o_xn + (size_t)npad * 4, 256);
+    const size_t need = o_st + (DP + 1) * 4;
+    if (need > h->knn_bytes) {  // grow-only scratch of the handle (split training set, norms, statistics)
+        CGP_CHECK(cudaStreamSynchronize(s));
+        if (h->knn_buf) CGP_CHECK(cudaFree(h->knn_buf));
+        h->knn_buf = nullptr;
+        h->knn_bytes = 0;
+        CGP_CHECK(cudaMalloc(&h->knn_buf, need));
+        h->knn_bytes = need;
+    }
+    char* buf = static_cast<char*>(h->knn_buf);
+    float2* Xp = reinterpret_cast<float2*>(buf);
+    float* xn = reinterpret_cast<float*>(buf + o_xn);
+    float* stats = reinterpret_cast<float*>(buf + o_st);
+    KL(h, CLS_KNN_PREP, s, k_knn_prep<DP><<<(unsigned)((npad + 255) / 256), 256, 0, s>>>(X, n, npad, d, Xp, xn));
+    KL(h, CLS_KNN_PREP, s, k_knn_stats<DP><<<1, 1024, 0, s>>>(X, n, d, stats));
+    const int sm = KTC_SMEM_BYTES(DP);
+    CGP_CHECK(cudaFuncSetAttribute(k_knn_tc<DP>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+    KL(h, CLS_KNN, s, k_knn_tc<DP><<<(unsigned)((M + KTC_QPB - 1) / KTC_QPB), 256, sm, s>>>(Xp, xn, stats, X, lab, n, npad, d, k, Q,
+                                                                                           M, out));
+    return (int)cudaGetLastError();
+}
+
 template <int D>
 static int launch_knn(HandleImpl* h, const double* X, const long long* lab, int n, int k, const double* Q, long long M, long long* out,
                       cudaStream_t s) {
@@ -810,8 +893,18 @@ static int launch_knn(HandleImpl* h, const double* X, const long long* lab, int 
         cudaError_t e = cudaFuncSetAttribute(k_knn<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
         if (e != cudaSuccess) return (int)e;
     }
+    bool tc = k <= 3 && n >= 2048 && M >= 4096;
+    if (h->knn_mode == 1) tc = false;
+    if (h->knn_mode == 2) tc = k <= 3;
     unsigned grid = (unsigned)((M + KNN_THREADS - 1) / KNN_THREADS);
-    KL(h, CLS_KNN, s, k_knn<D><<<grid, KNN_THREADS, sm, s>>>(X, lab, n, k, Q, M, out));
+    if (tc) {
+        int rc = D <= 8 ? launch_knn_tc<8>(h, X, lab, n, D, k, Q, M, out, s) : launch_knn_tc<16>(h, X, lab, n, D, k, Q, M, out, s);
+        if (rc) return rc;
+        // queries the prefilter could not certify (out = -1): exact brute force; blocks without one exit at once
+        KL(h, CLS_KNN_EXACT, s, k_knn<D><<<grid, KNN_THREADS, sm, s>>>(X, lab, n, k, Q, M, out, 1));
+        return (int)cudaGetLastError();
+    }
+    KL(h, CLS_KNN_EXACT, s, k_knn<D><<<grid, KNN_THREADS, sm, s>>>(X, lab, n, k, Q, M, out, 0));
     return (int)cudaGetLastError();
 }
 
@@ -897,7 +990,8 @@ static int run_score(HandleImpl* h, int kind, const double* X, const int64_t* of
                      const double* W, const double* alpha_vec, const double* y_mean, const double* y_std,
                      const double* y_max, const double* Q, const int64_t* qlabel, int64_t m, int64_t idx_base,
                      double* score, double* mean, double* std_, double* best_score, int64_t* best_idx,
-                     int64_t* best_cluster, void* workspace, size_t ws_bytes, cudaStream_t s, bool prune = false) {
+                     int64_t* best_cluster, void* workspace, size_t ws_bytes, cudaStream_t s, bool prune = false,
+                     const double* penalty = nullptr) {
     if (C > 4096) return -5;
     ScoreLayout L = score_layout(offs, C, d, m);
     if (L.total > ws_bytes) return -100;
@@ -945,11 +1039,11 @@ static int run_score(HandleImpl* h, int kind, const double* X, const int64_t* of
             KL(h, CLS_MEAN, s, k_mean<<<(unsigned)((rows + 7) / 8), 256, 0, s>>>(kstar, alpha_vec + offs[c], (int)n, (int)npad, rows, mraw));
             if (prune) {  // mean-only bound -> survivors -> exact variance / score of the survivors -> tighter bound
                 KL(h, CLS_SCORE_FINISH, s, k_prune_select<<<1, 1024, 0, s>>>(mraw, rows, th, d, y_mean, y_std, y_max, c, (double)n, lb,
-                                                                              sel, cnt, sorted + p0));
+                                                                              sel, cnt, sorted + p0, penalty, perm + p0));
                 KL(h, CLS_PREDICT_VNORM, s, k_predict_vnorm_sel<<<(unsigned)((rows_pad / CGP_TILE) * T), CGP_GEMM_THREADS, GEMM_SMEM_BYTES, s>>>(
                     Wc, kstar, vpart, (int)npad, L.mch, sel, cnt));
                 KL(h, CLS_SCORE_FINISH, s, k_score_finish_sel<<<(unsigned)((rows + 255) / 256), 256, 0, s>>>(
-                    vpart, L.mch, T, mraw, sel, cnt, th, d, y_mean, y_std, y_max, c, (double)n, sorted + p0));
+                    vpart, L.mch, T, mraw, sel, cnt, th, d, y_mean, y_std, y_max, c, (double)n, sorted + p0, penalty, perm + p0));
                 KL(h, CLS_SCORE_FINISH, s, k_lb_update<<<1, 1024, 0, s>>>(sorted + p0, rows, lb));
                 continue;
             }
@@ -960,7 +1054,7 @@ static int run_score(HandleImpl* h, int kind, const double* X, const int64_t* of
                 KL(h, CLS_PREDICT_VNORM, s, k_predict_vnorm<<<(unsigned)((rows_pad / CGP_TILE) * T), CGP_GEMM_THREADS, GEMM_SMEM_BYTES, s>>>(
                     Wc, kstar, vpart, (int)npad, L.mch));
             KL(h, CLS_SCORE_FINISH, s, k_score_finish<<<(unsigned)((rows + 255) / 256), 256, 0, s>>>(
-                vpart, L.mch, need_var ? T : 0, mraw, rows, p0, perm, th, d, y_mean, y_std, y_max, c, (double)n, mean, std_, score, sorted));
+                vpart, L.mch, need_var ? T : 0, mraw, rows, p0, perm, th, d, y_mean, y_std, y_max, c, (double)n, mean, std_, score, sorted, penalty));
         }
     }
     if (y_max && best_score && best_idx && best_cluster) {
@@ -1000,8 +1094,9 @@ extern "C" int cgp_predict(cgp_handle* hh, int kind, const double* X, const int6
 extern "C" int cgp_ei_argmax(cgp_handle* hh, int kind, const double* X, const int64_t* offs, int C, int d,
                              const double* theta, const double* W, const double* alpha_vec, const double* y_mean,
                              const double* y_std, const double* y_max, const double* Q, const int64_t* qlabel, int64_t m,
-                             int64_t idx_base, double* score, double* mean, double* std_, double* best_score,
-                             int64_t* best_idx, int64_t* best_cluster, void* workspace, size_t ws_bytes, void* stream) {
+                             int64_t idx_base, const double* penalty, double* score, double* mean, double* std_,
+                             double* best_score, int64_t* best_idx, int64_t* best_cluster, void* workspace, size_t ws_bytes,
+                             void* stream) {
     CGP_ENTER(hh);
     if (kind != 0 && kind != 1) return -2;
     if (!X) return -3;
@@ -1021,13 +1116,13 @@ extern "C" int cgp_ei_argmax(cgp_handle* hh, int kind, const double* X, const in
     if (!best_cluster) return -22;
     if (!workspace) return -23;
     return run_score(h, kind, X, offs, C, d, theta, W, alpha_vec, y_mean, y_std, y_max, Q, qlabel, m, idx_base, score, mean,
-                     std_, best_score, best_idx, best_cluster, workspace, ws_bytes, (cudaStream_t)stream);
+                     std_, best_score, best_idx, best_cluster, workspace, ws_bytes, (cudaStream_t)stream, false, penalty);
 }
 
 extern "C" int cgp_ei_argmax_pruned(cgp_handle* hh, int kind, const double* X, const int64_t* offs, int C, int d,
                                     const double* theta, const double* W, const double* alpha_vec, const double* y_mean,
                                     const double* y_std, const double* y_max, const double* Q, const int64_t* qlabel,
-                                    int64_t m, int64_t idx_base, double* best_score, int64_t* best_idx,
+                                    int64_t m, int64_t idx_base, const double* penalty, double* best_score, int64_t* best_idx,
                                     int64_t* best_cluster, void* workspace, size_t ws_bytes, void* stream) {
     CGP_ENTER(hh);
     if (kind != 0 && kind != 1) return -2;
@@ -1048,7 +1143,8 @@ extern "C" int cgp_ei_argmax_pruned(cgp_handle* hh, int kind, const double* X, c
     if (!best_cluster) return -19;
     if (!workspace) return -20;
     return run_score(h, kind, X, offs, C, d, theta, W, alpha_vec, y_mean, y_std, y_max, Q, qlabel, m, idx_base, nullptr,
-                     nullptr, nullptr, best_score, best_idx, best_cluster, workspace, ws_bytes, (cudaStream_t)stream, true);
+                     nullptr, nullptr, best_score, best_idx, best_cluster, workspace, ws_bytes, (cudaStream_t)stream, true,
+                     penalty);
 }
 
 extern "C" int cgp_rowdot(cgp_handle* hh, const double* A, const double* B, int64_t rows, int64_t n, int64_t ld, double* out,

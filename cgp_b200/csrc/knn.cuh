@@ -12,12 +12,15 @@
 template <int D>
 __global__ void __launch_bounds__(KNN_THREADS)
 k_knn(const double* __restrict__ X, const long long* __restrict__ lab, int n, int k, const double* __restrict__ Q, long long M,
-      long long* __restrict__ out) {
+      long long* __restrict__ out, int only_flagged) {
     extern __shared__ __align__(16) double sm[];
     double* xs = sm;                                          // [KNN_TILE][D]
     int* ls = reinterpret_cast<int*>(sm + KNN_TILE * D);      // [KNN_TILE]
     const long long q = (long long)blockIdx.x * KNN_THREADS + threadIdx.x;
-    const bool active = q < M;
+    // only_flagged: second pass behind the tensor-core prefilter (knn_tc.cuh): only queries it could not certify
+    // (out[q] == -1) are computed; blocks without one exit at once
+    const bool active = q < M && (!only_flagged || out[q] == -1);
+    if (only_flagged && !__syncthreads_or(active)) return;
     double qv[D];
 #pragma unroll
     for (int p = 0; p < D; ++p) qv[p] = active ? Q[q * D + p] : 0.0;

@@ -119,7 +119,7 @@ k_score_finish(const double* __restrict__ vpart, long long vstride, int T, const
                long long rows, long long pos0, const long long* __restrict__ perm, const double* __restrict__ th, int d,
                const double* __restrict__ ymean, const double* __restrict__ ystd, const double* __restrict__ ymax,
                int cluster, double n_c, double* __restrict__ mean_out, double* __restrict__ std_out,
-               double* __restrict__ score_out, double* __restrict__ score_sorted) {
+               double* __restrict__ score_out, double* __restrict__ score_sorted, const double* __restrict__ penalty) {
     const long long r = (long long)blockIdx.x * 256 + threadIdx.x;
     if (r >= rows) return;
     double vs = 0.0;
@@ -134,7 +134,8 @@ k_score_finish(const double* __restrict__ vpart, long long vstride, int T, const
     if (mean_out) mean_out[orig] = mu;
     if (std_out) std_out[orig] = sd;
     if (ymax) {
-        const double sc = ei_value(mu, sd, ymax[cluster]) / n_c;  // acquisition.py:32
+        // acquisition.py:29-32: (EI + boundary_penalty) / n_c ; penalty is indexed by the caller's candidate order
+        const double sc = (penalty ? ei_value(mu, sd, ymax[cluster]) + penalty[orig] : ei_value(mu, sd, ymax[cluster])) / n_c;
         if (score_out) score_out[orig] = sc;
         score_sorted[pos0 + r] = sc;
     }
@@ -153,7 +154,7 @@ __global__ void __launch_bounds__(1024)
 k_prune_select(const double* __restrict__ mraw, long long rows, const double* __restrict__ th, int d,
                const double* __restrict__ ymean, const double* __restrict__ ystd, const double* __restrict__ ymax,
                int cluster, double n_c, const double* __restrict__ lb, int* __restrict__ sel, int* __restrict__ count,
-               double* __restrict__ score_chunk) {
+               double* __restrict__ score_chunk, const double* __restrict__ penalty, const long long* __restrict__ perm_chunk) {
     __shared__ int part[1024];
     const int per = (int)((rows + 1023) / 1024);
     const long long s = (long long)threadIdx.x * per, e = min(rows, s + per);
@@ -163,8 +164,11 @@ k_prune_select(const double* __restrict__ mraw, long long rows, const double* __
     unsigned long long keep = 0ull;  // per <= 64 (chunks hold at most 65536 candidates)
     int c = 0;
     for (long long r = s; r < e; ++r) {
-        const double ub = ei_value(ys * mraw[r] + ym, sd_prior, yx) / n_c;
-        const bool k = !(ub * (1.0 + 1e-9) + 1e-300 < bound);
+        double ub = ei_value(ys * mraw[r] + ym, sd_prior, yx);
+        // the additive penalty shifts bound and score alike; the 1e-9 inflation is applied to the EI part only
+        const double pen = penalty ? penalty[perm_chunk[r]] : 0.0;
+        ub = (ub * (1.0 + 1e-9) + 1e-300 + pen) / n_c;
+        const bool k = !(ub + 1e-15 * fabs(ub) < bound);
         if (k) {
             keep |= 1ull << (int)(r - s);
             ++c;
@@ -194,7 +198,8 @@ __global__ void __launch_bounds__(256)
 k_score_finish_sel(const double* __restrict__ vpart, long long vstride, int T, const double* __restrict__ mraw,
                    const int* __restrict__ sel, const int* __restrict__ count, const double* __restrict__ th, int d,
                    const double* __restrict__ ymean, const double* __restrict__ ystd, const double* __restrict__ ymax,
-                   int cluster, double n_c, double* __restrict__ score_chunk) {
+                   int cluster, double n_c, double* __restrict__ score_chunk, const double* __restrict__ penalty,
+                   const long long* __restrict__ perm_chunk) {
     const int q = blockIdx.x * 256 + threadIdx.x;
     if (q >= *count) return;
     const int r = sel[q];
@@ -206,7 +211,7 @@ k_score_finish_sel(const double* __restrict__ vpart, long long vstride, int T, c
     const double ys = ystd[cluster];
     const double sd = sqrt(var * (ys * ys));
     const double mu = ys * mraw[r] + ymean[cluster];
-    score_chunk[r] = ei_value(mu, sd, ymax[cluster]) / n_c;
+    score_chunk[r] = (penalty ? ei_value(mu, sd, ymax[cluster]) + penalty[perm_chunk[r]] : ei_value(mu, sd, ymax[cluster])) / n_c;
 }
 
 // lb = max(lb, max over the chunk's exact scores).  One block of 1024.

@@ -82,9 +82,50 @@ class cGP_constrained(object):
         return Y
 
     def candidate_mask(self, Q):
-        """Hard constraints as a candidate filter (replaces the Linear/NonlinearConstraint objects handed to
-        trust-constr, REF/cGP/cGP_constrained_module.py:202-223).  Return a bool array [M]; default keeps all."""
+        """Extra hard constraints as a candidate filter (a hook of this backend).  Return a bool array [M]; default keeps
+        all.  The reference's own constraint objects are honoured through get_linear_constraint /
+        get_nonlinear_constraint / get_bounds (see constraint_mask)."""
         return None
+
+    def get_linear_constraint(self):
+        """scipy.optimize.LinearConstraint or None (REF/cGP/cGP_constrained_module.py:220-222)."""
+        return None
+
+    def get_nonlinear_constraint(self):
+        """scipy.optimize.NonlinearConstraint or None (REF/cGP/cGP_constrained_module.py:202-206)."""
+        return None
+
+    def constraint_mask(self, Q, bounds):
+        """The hard constraints the reference hands to trust-constr (REF/cGP/cGP_constrained.py:362-366:
+        ``constraints=[linear_constraint, nonlinear_constraint], bounds=bounds_constraint``) as a filter of the dense
+        candidate set: keep q iff  lb <= A q <= ub,  lb <= fun(q) <= ub  and  bounds.lb <= q <= bounds.ub.
+        ``fun`` is tried vectorised (columns = candidates, the SciPy convention) and verified on a few points against
+        point-wise calls; a function that only works on one point is called per candidate."""
+        keep = np.ones(Q.shape[0], dtype=bool)
+        lin, nonlin = self.get_linear_constraint(), self.get_nonlinear_constraint()
+        if lin is not None:
+            A = np.atleast_2d(np.asarray(lin.A, dtype=np.float64))
+            v = Q @ A.T
+            keep &= np.all((v >= np.asarray(lin.lb, dtype=np.float64)) & (v <= np.asarray(lin.ub, dtype=np.float64)), axis=1)
+        if nonlin is not None:
+            fun = nonlin.fun
+            lb, ub = np.atleast_1d(np.asarray(nonlin.lb, dtype=np.float64)), np.atleast_1d(np.asarray(nonlin.ub, dtype=np.float64))
+            if not (np.all(np.isneginf(lb)) and np.all(np.isposinf(ub))):
+                point = lambda q: np.atleast_1d(np.asarray(fun(q), dtype=np.float64))  # noqa: E731
+                vals = None
+                try:
+                    v = np.asarray(fun(Q.T), dtype=np.float64)
+                    v = v.reshape(1, -1) if v.ndim <= 1 else v
+                    if v.shape[1] == Q.shape[0] and v.size and all(
+                            np.allclose(v[:, j], point(Q[j]), rtol=1e-12, atol=0.0) for j in range(0, Q.shape[0], max(1, Q.shape[0] // 8))):
+                        vals = v.T
+                except Exception:  # noqa: BLE001
+                    vals = None
+                if vals is None:
+                    vals = np.stack([point(q) for q in Q])
+                keep &= np.all((vals >= lb) & (vals <= ub), axis=1)
+        keep &= np.all((Q >= bounds[:, 0]) & (Q <= bounds[:, 1]), axis=1)
+        return keep
 
     def recode(self, label):
         level = np.unique(np.array(label))
@@ -121,11 +162,14 @@ class cGP_constrained(object):
 
     def _candidates(self, bounds):
         Q = np.random.uniform(bounds[:, 0], bounds[:, 1], size=(int(self.N_CANDIDATES), bounds.shape[0]))
+        keep = self.constraint_mask(Q, bounds)
         mask = self.candidate_mask(Q)
         if mask is not None:
-            Q = Q[np.asarray(mask, dtype=bool)]
+            keep &= np.asarray(mask, dtype=bool)
+        if not np.all(keep):
+            Q = Q[keep]
             if Q.shape[0] == 0:
-                raise RuntimeError("candidate_mask rejected every candidate")
+                raise RuntimeError("the constraints (linear / nonlinear / bounds / candidate_mask) reject every candidate")
         return Q
 
     def run(self):
@@ -168,8 +212,8 @@ class cGP_constrained(object):
                     mode = "acquisition"
                 fitted_n, fitted_labels = n, labels.copy()
                 Q = self._candidates(bounds)
-                pen = self.boundary_penalty(Q, X)
                 if self.ACQUISITION == "MSPE":  # minimised, REF/cGP/acquisition.py:69-75
+                    pen = self.boundary_penalty(Q, X)
                     if np.isscalar(pen) and pen == 0:
                         X_next, score, idx = model.select_next_mspe(Q)
                     else:
@@ -177,15 +221,8 @@ class cGP_constrained(object):
                         sc = model.mspe_candidates(Q) + np.asarray(pen, dtype=np.float64) / np.bincount(labels)[lab_q]
                         idx = int(np.lexsort((np.arange(sc.shape[0]), lab_q, sc))[0])
                         X_next, score = Q[idx], float(sc[idx])
-                elif np.isscalar(pen) and pen == 0:
-                    X_next, score, idx = model.select_next(Q, prune=bool(self.PRUNED_SCAN))
-                else:  # soft constraint: EI + penalty, then / n_c (REF/cGP/acquisition.py:29-32)
-                    out = model.score_candidates(Q)
-                    n_c = np.bincount(labels)[out["labels"]]
-                    sc = out["score"] + np.asarray(pen, dtype=np.float64) / n_c
-                    order = np.lexsort((np.arange(sc.shape[0]), out["labels"], -sc))
-                    idx = int(order[0])
-                    X_next, score = Q[idx], float(sc[idx])
+                else:  # soft constraint inside the GPU score: (EI + boundary_penalty(x, X_c)) / n_c (REF/cGP/acquisition.py:29-32)
+                    X_next, score, idx = model.select_next(Q, prune=bool(self.PRUNED_SCAN), boundary_penalty=self.boundary_penalty)
                 self.history.append(dict(step=it, mode=mode, score=float(score), n_clusters=int(labels.max()) + 1))
             else:  # random search inside the bounds (:380-412)
                 X_next = np.random.uniform(bounds[:, 0], bounds[:, 1])
@@ -291,6 +328,13 @@ def main(argv=None):
 
         def candidate_mask(self, Q):
             return ft.candidate_mask(Q) if hasattr(ft, "candidate_mask") else None
+
+        # constraint objects a reference -f module exports at module level (REF/cGP/f_truth.py:44-59)
+        def get_linear_constraint(self):
+            return getattr(ft, "linear_constraint", None)
+
+        def get_nonlinear_constraint(self):
+            return getattr(ft, "nonlinear_constraint", None)
 
         def f_Cluster(self, seed):
             if o.CLUSTER is not None:  # -C <module>: f_Cluster(RND_SEED) (REF/cGP/cluster.py:3-15)

@@ -15,7 +15,9 @@ import numpy as np
 import torch
 
 from . import _lib, dist as cdist
-from .lbfgs import minimize_lockstep
+from .lbfgs import StealBoard, minimize_async, minimize_lockstep
+
+_FIT_EPOCH = [0]  # per-process count of sharded fits: key prefix of the work-stealing board (same on every rank)
 
 LOG_LO = math.log(1e-5)  # REF/cGP/cGP_constrained.py:169
 LOG_HI = math.log(1e5)
@@ -93,19 +95,41 @@ class ClusterGPEngine:
         self.theta = None
         self.model = None
         self._ws = None
+        self._ws_lane = {}      # lane id (>= 1) -> workspace of that evaluation lane
+        self._lane_streams = {}
         self._ws_capped = False
         self._slots = []
         self.fit_stats = {}
 
     # ------------------------------------------------------------------ workspace
-    def _workspace(self, nbytes, partial_ok=False):
-        """Grow-only scratch buffer.  partial_ok: the caller (batched LML) can work in chunks with less than nbytes."""
+    def _workspace(self, nbytes, partial_ok=False, lane=0):
+        """Grow-only scratch buffer (one per evaluation lane; lane 0 also serves every non-fit call).
+        partial_ok: the caller (batched LML) can work in chunks with less than nbytes."""
+        if lane:
+            ws = self._ws_lane.get(lane)
+            have = 0 if ws is None else ws.numel()
+            if have >= nbytes or (self._ws_capped and have > 0):
+                return ws
+            free, _total = torch.cuda.mem_get_info(self.device)
+            want = min(nbytes, int((free + have) * self.mem_fraction * 0.5))
+            if want > have:
+                self._ws_lane[lane] = None
+                self._ws_lane[lane] = torch.empty(want, dtype=torch.uint8, device=self.device)
+            if want < nbytes:
+                self._ws_capped = True
+            return self._ws_lane[lane]
         have = 0 if self._ws is None else self._ws.numel()
         if have >= nbytes or (partial_ok and self._ws_capped and have > 0):
             return self._ws
         # cudaMemGetInfo is slow (measured: up to 59 ms per call on a busy B200) -> only when the workspace must grow
         free, _total = torch.cuda.mem_get_info(self.device)
         budget = int((free + have) * self.mem_fraction)
+        if partial_ok:
+            # the fit's evaluation workspace must leave room for what follows it: the factors L and W of the final model
+            # (configs[3]: 2 x 34 GB) next to the factorisation workspace, which reuses this buffer
+            reserve = 16 * _lib.model_elems(self.offs)
+            one_pair = max(_lib.lml_workspace_bytes(self.offs, np.asarray([c], dtype=np.int32), self.d) for c in range(self.C))
+            budget = max(budget - reserve, min(one_pair, budget))
         want = min(nbytes, budget)
         if want < nbytes and not partial_ok:
             raise _lib.CgpError(f"out of device memory: this call needs a {nbytes / 2**30:.2f} GiB workspace, the budget is "
@@ -140,21 +164,42 @@ class ClusterGPEngine:
         self._slots = [s for s in self._slots if s["busy"] or s["cap"] >= cap] + [slot]  # drop outgrown free slots
         return slot
 
-    def lml_grad_submit(self, pair_cluster, thetas, want_grad=True):
+    def _lane_stream(self, lane):
+        """Lane 0 = the caller's current stream; every further lane owns a torch stream (and a library handle with its
+        own internal streams), so that batches of different lanes run concurrently on the device."""
+        if lane == 0:
+            return torch.cuda.current_stream(self.device)
+        st = self._lane_streams.get(lane)
+        if st is None:
+            st = self._lane_streams[lane] = torch.cuda.Stream(self.device)
+        return st
+
+    def lml_grad_submit(self, pair_cluster, thetas, want_grad=True, lane=0):
         """Enqueue a batched LML (+ gradient) evaluation and the device->pinned-host copies of its results.
         Returns a ticket for lml_grad_collect; nothing here waits for the device."""
+        if lane:
+            with torch.cuda.stream(self._lane_stream(lane)):
+                return self._lml_grad_submit(pair_cluster, thetas, want_grad, lane)
+        return self._lml_grad_submit(pair_cluster, thetas, want_grad, 0)
+
+    def lml_grad_done(self, ticket):
+        """Non-blocking: has the evaluation of `ticket` finished?"""
+        return ticket[0]["ev"].query()
+
+    def _lml_grad_submit(self, pair_cluster, thetas, want_grad, lane):
         pair_cluster = np.asarray(pair_cluster, dtype=np.int32)
         B = len(pair_cluster)
         thetas = np.asarray(thetas, dtype=np.float64).reshape(B, self.P)
         need = _lib.lml_workspace_bytes(self.offs, pair_cluster, self.d)
-        ws = self._workspace(need, partial_ok=True)
+        ws = self._workspace(need, partial_ok=True, lane=lane)
         slot = self._eval_slot(B)
         slot["busy"] = True
         slot["th_h"].numpy()[:B] = thetas
         th = slot["th"][:B]
         th.copy_(slot["th_h"][:B], non_blocking=True)
         out = (slot["lml"][:B], slot["grad"][:B], slot["info"][:B])
-        _lib.lml_grad_batched(self.Xs, self.yn, self.offs, pair_cluster, th, self.alpha, self.kind, ws, want_grad, out=out)
+        _lib.lml_grad_batched(self.Xs, self.yn, self.offs, pair_cluster, th, self.alpha, self.kind, ws, want_grad, out=out,
+                              lane=lane)
         slot["lml_h"][:B].copy_(out[0], non_blocking=True)
         if want_grad:
             slot["grad_h"][:B].copy_(out[1], non_blocking=True)
@@ -181,19 +226,26 @@ class ClusterGPEngine:
 
     # ------------------------------------------------------------------ fit
     def fit(self, n_restarts, seed=0, theta0=None, bounds=None, optimize=True, shard_mode=None, max_lockstep=None):
-        """All clusters x (R+1) restarts in lock-step (SK/_gpr.py:296-340), sharded over ranks, then the final
-        factorisation at each cluster's best theta (SK/_gpr.py:349-367).
+        """All clusters x (R+1) L-BFGS-B runs (SK/_gpr.py:296-340) with batched GPU evaluations, sharded over ranks, then
+        the final factorisation at each cluster's best theta (SK/_gpr.py:349-367).
 
-        shard_mode "balanced" (default): every rank keeps all state machines and in each lock-step evaluates only its
-        share of the waiting runs, one all-reduce of (f, g) per lock-step (see lbfgs.minimize_lockstep); the work stays
-        even although run lengths range from 2 to 167 evaluations.  "static": the (cluster, restart) pairs are dealt
-        round-robin once, each rank optimises its own pairs, one all-gather of (theta*, -lml) rows follows.
-        Measured on 8 B200, config 3: balanced 2.62 s / iteration, static 2.70 s (its slowest rank draws 754 of the 4938
-        evaluations, mean 617).  Both select the same point with the same score bits.
-        max_lockstep: cut the optimisation after that many lock-steps (each run keeps its best evaluated theta): the
-        single-65536-sample-cluster configuration measures ONE lock-step of its R+1 runs (9 s per evaluation)."""
+        shard_mode (env CGP_SHARD_MODE):
+        * "async" (default): every rank OWNS whole runs and advances them without waiting for any other rank; inside a
+          rank up to CGP_LANES (2) evaluation lanes run concurrently (the latency-bound chain of one lane's
+          factorisations overlaps the bulk of the other's, and the host advances one lane's state machines while the
+          device works on the other); a rank that runs short of runs steals ready ones from the busiest rank over the
+          c10d store (lbfgs.StealBoard).  One all-reduce of the (theta*, -lml) table at the end.  No per-step exchange,
+          no ceil(active / world) quantisation, no rank waits for the slowest evaluation of another.
+        * "balanced": every rank keeps all state machines; each global lock-step deals the waiting runs to the ranks and
+          all-reduces (f, g) (round-1 default; 8 B200, config 3: 2.62 s / iteration).
+        * "static": pairs dealt round-robin once, no exchange until the final all-gather (2.70 s; its slowest rank draws
+          754 of the 4938 evaluations, mean 617).
+        Every run sees the same sequence of (theta -> f, g) in every mode and on any number of ranks (the kernels are
+        batch-invariant bit for bit), so the selected point and its score bits do not depend on the mode.
+        max_lockstep: cut every run after that many evaluations (it keeps its best evaluated theta): the
+        single-65536-sample-cluster configuration measures ONE evaluation of each of its R+1 runs (9 s each)."""
         if shard_mode is None:
-            shard_mode = os.environ.get("CGP_SHARD_MODE", "balanced")
+            shard_mode = os.environ.get("CGP_SHARD_MODE", "async")
         rank, ws = cdist.world()
         P, C = self.P, self.C
         self._ws_capped = False
@@ -213,27 +265,110 @@ class ClusterGPEngine:
             self._factorize()
             return self
         n_pairs = C * R1  # pair p = (cluster p // R1, run p % R1)
-        balanced = ws > 1 and shard_mode == "balanced"
-        mine = list(range(n_pairs)) if balanced else cdist.my_pairs(n_pairs, rank, ws)
-        pc_all = np.asarray([p // R1 for p in mine], dtype=np.int32)
-        x0s = [starts[p % R1] if (start0 is None or p % R1) else start0[p // R1] for p in mine]
+        pair_c = np.arange(n_pairs, dtype=np.int32) // R1
         n_eval = [0]
         t_eval = [0.0]
         evals_c = np.zeros(C, dtype=np.int64)  # evaluations THIS rank performed, per cluster
         t_fit0 = time.perf_counter()
+        x0_of = lambda p: starts[p % R1] if (start0 is None or p % R1) else start0[p // R1]  # noqa: E731
+        gc_was_on = gc.isenabled()
+        gc.disable()  # thousands of live L-BFGS-B machines: a generation-2 sweep inside a lock-step costs tens of ms
+        extra = {}
+        try:
+            if shard_mode == "async":
+                table, steps, extra = self._fit_async(n_pairs, pair_c, x0_of, lo, hi, rank, ws, max_lockstep, n_eval, t_eval,
+                                                      evals_c)
+                mode = "async"
+            else:
+                balanced = ws > 1 and shard_mode == "balanced"
+                mine = list(range(n_pairs)) if balanced else cdist.my_pairs(n_pairs, rank, ws)
+                pc_all = pair_c[mine]
 
-        def eval_batch(idx, Xs):
-            t0 = time.perf_counter()
-            lml, grad, _ = self.lml_grad(pc_all[idx], Xs, True)
-            n_eval[0] += len(idx)
-            np.add.at(evals_c, pc_all[idx], 1)
-            t_eval[0] += time.perf_counter() - t0
-            return -lml, -grad
+                def eval_batch(idx, Xs):
+                    t0 = time.perf_counter()
+                    lml, grad, _ = self.lml_grad(pc_all[idx], Xs, True)
+                    n_eval[0] += len(idx)
+                    np.add.at(evals_c, pc_all[idx], 1)
+                    t_eval[0] += time.perf_counter() - t0
+                    return -lml, -grad
 
-        def submit(idx, Xs):
-            n_eval[0] += len(idx)
-            np.add.at(evals_c, pc_all[idx], 1)
-            return self.lml_grad_submit(pc_all[idx], Xs, True)
+                def submit(idx, Xs):
+                    n_eval[0] += len(idx)
+                    np.add.at(evals_c, pc_all[idx], 1)
+                    return self.lml_grad_submit(pc_all[idx], Xs, True)
+
+                def collect(ticket):
+                    t0 = time.perf_counter()
+                    lml, grad, _ = self.lml_grad_collect(ticket)
+                    t_eval[0] += time.perf_counter() - t0
+                    return -lml, -grad
+
+                shard = None
+                if balanced:
+                    def allreduce(buf):
+                        t = torch.from_numpy(buf).to(self.device)
+                        torch.distributed.all_reduce(t)
+                        return t.cpu().numpy()
+
+                    shard = dict(rank=rank, world=ws, cost=self.counts[pc_all].astype(np.float64) ** 3, allreduce=allreduce)
+                xs, fs, nfev, nit, steps = minimize_lockstep(
+                    eval_batch, [x0_of(p) for p in mine], lo, hi, submit=submit, collect=collect,
+                    pipeline_min=int(os.environ.get("CGP_PIPELINE_MIN", "256")), shard=shard,
+                    **({} if max_lockstep is None else {"max_steps": int(max_lockstep)}))
+                rows = np.concatenate([xs, fs[:, None], nfev[:, None], nit[:, None]], axis=1).reshape(len(mine), P + 3)
+                if balanced:  # every rank already holds every run's result
+                    table = rows
+                else:
+                    table = cdist.gather_pair_rows(torch.from_numpy(rows).to(self.device), n_pairs, rank, ws).cpu().numpy()
+                mode = "balanced" if balanced else "static"
+        finally:
+            if gc_was_on:
+                gc.enable()
+        t_opt = time.perf_counter() - t_fit0
+        table = table.reshape(C, R1, P + 3)
+        self.run_thetas = table[:, :, :P]
+        self.run_values = table[:, :, P]
+        best = np.argmin(self.run_values, axis=1)  # first minimum in run order, SK/_gpr.py:336-337
+        self.theta = np.stack([self.run_thetas[c, best[c]] for c in range(C)])
+        self.fit_stats = dict(lockstep=steps, evals=int(n_eval[0]), nfev=table[:, :, P + 1].reshape(-1).astype(np.int64),
+                              nit=table[:, :, P + 2].reshape(-1).astype(np.int64), pairs_total=n_pairs, eval_s=t_eval[0],
+                              optimizer_host_s=t_opt - t_eval[0], evals_per_cluster=evals_c, shard_mode=mode, **extra)
+        self._factorize()
+        return self
+
+    def _fit_async(self, n_pairs, pair_c, x0_of, lo, hi, rank, ws, max_evals, n_eval, t_eval, evals_c):
+        """Body of shard_mode "async" (see fit): -> (result table [n_pairs, P + 3], lane steps, extra stats)."""
+        P = self.P
+        n_lanes = max(1, int(os.environ.get("CGP_LANES", "2")))
+        lane_max = int(os.environ.get("CGP_LANE_MAX", "48"))
+        pipe_min = int(os.environ.get("CGP_PIPELINE_MIN", "256"))
+        # a single pair that needs a large share of the device memory (configs[3]: 69 GB) leaves no room for a 2nd lane
+        big = max(_lib.lml_workspace_bytes(self.offs, np.asarray([c], dtype=np.int32), self.d) for c in range(self.C))
+        free, _ = torch.cuda.mem_get_info(self.device)
+        if big * 4 > free * self.mem_fraction:
+            n_lanes = 1
+        # initial deal: heaviest runs first, round-robin (costs ~ n_c^3)
+        order = np.argsort(-(self.counts[pair_c].astype(np.float64) ** 3), kind="stable")
+        mine = np.sort(order[rank::ws])
+        cur = torch.cuda.current_stream(self.device)
+        for lane in range(1, n_lanes):
+            self._lane_stream(lane).wait_stream(cur)  # the training arrays were uploaded on the caller's stream
+        multi = [False]
+
+        def lane_policy(active):
+            # many runs: two lanes hide the host's L-BFGS-B work behind the device; few runs: two lanes overlap the
+            # latency-bound chain of one batch with the bulk of the other; in between one batch fills the device
+            use = n_lanes if (active > pipe_min or active <= lane_max) else 1
+            multi[0] = use > 1
+            return use
+
+        def submit(lane, gid, X):
+            pc = pair_c[gid]
+            n_eval[0] += len(gid)
+            np.add.at(evals_c, pc, 1)
+            if n_lanes > 1:
+                _lib.profile_mute(multi[0], self.device.index, lane)  # concurrent lanes: event brackets not exclusive
+            return self.lml_grad_submit(pc, X, True, lane=lane)
 
         def collect(ticket):
             t0 = time.perf_counter()
@@ -241,40 +376,29 @@ class ClusterGPEngine:
             t_eval[0] += time.perf_counter() - t0
             return -lml, -grad
 
-        shard = None
-        if balanced:
-            def allreduce(buf):
-                t = torch.from_numpy(buf).to(self.device)
-                torch.distributed.all_reduce(t)
-                return t.cpu().numpy()
+        board = None
+        if ws > 1:
+            from torch.distributed.distributed_c10d import _get_default_store
 
-            shard = dict(rank=rank, world=ws, cost=self.counts[pc_all].astype(np.float64) ** 3, allreduce=allreduce)
-        gc_was_on = gc.isenabled()
-        gc.disable()  # thousands of live L-BFGS-B machines: a generation-2 sweep inside a lock-step costs tens of ms
-        try:
-            xs, fs, nfev, nit, steps = minimize_lockstep(eval_batch, x0s, lo, hi, submit=submit, collect=collect,
-                                                         pipeline_min=int(os.environ.get("CGP_PIPELINE_MIN", "256")),
-                                                         shard=shard, **({} if max_lockstep is None else
-                                                                         {"max_steps": int(max_lockstep)}))
-        finally:
-            if gc_was_on:
-                gc.enable()
-        t_opt = time.perf_counter() - t_fit0
-        rows = np.concatenate([xs, fs[:, None]], axis=1).reshape(len(mine), P + 1)
-        if balanced:  # every rank already holds every run's result
-            table = rows.reshape(C, R1, P + 1)
-        else:
-            table = cdist.gather_pair_rows(torch.from_numpy(rows).to(self.device), n_pairs, rank, ws)
-            table = table.cpu().numpy().reshape(C, R1, P + 1)
-        self.run_thetas = table[:, :, :P]
-        self.run_values = table[:, :, P]
-        best = np.argmin(self.run_values, axis=1)  # first minimum in run order, SK/_gpr.py:336-337
-        self.theta = np.stack([self.run_thetas[c, best[c]] for c in range(C)])
-        self.fit_stats = dict(lockstep=steps, evals=int(n_eval[0]), nfev=nfev, nit=nit, pairs_local=len(mine),
-                              pairs_total=n_pairs, eval_s=t_eval[0], optimizer_host_s=t_opt - t_eval[0],
-                              evals_per_cluster=evals_c, shard_mode=("balanced" if balanced else "static"))
-        self._factorize()
-        return self
+            _FIT_EPOCH[0] += 1
+            board = StealBoard(_get_default_store(), f"cgp_b200/fit{_FIT_EPOCH[0]}", rank, ws, n_pairs)
+        finished, st = minimize_async([x0_of(int(p)) for p in mine], mine, lo, hi, submit, self.lml_grad_done, collect,
+                                      n_lanes=n_lanes, lane_policy=lane_policy, board=board, max_evals=max_evals)
+        for lane in range(1, n_lanes):
+            if n_lanes > 1:
+                _lib.profile_mute(False, self.device.index, lane)
+            cur.wait_stream(self._lane_stream(lane))
+        if n_lanes > 1:
+            _lib.profile_mute(False, self.device.index, 0)
+        table = np.zeros((n_pairs, P + 3))
+        for gid, (x, f, nfev, nit) in finished.items():
+            table[gid, :P], table[gid, P], table[gid, P + 1], table[gid, P + 2] = x, f, nfev, nit
+        if ws > 1:  # every run finished on exactly one rank: the sum over ranks is the full table (exact: + 0.0)
+            t = torch.from_numpy(table).to(self.device)
+            torch.distributed.all_reduce(t)
+            table = t.cpu().numpy()
+        return table, st["steps"], dict(lanes=n_lanes, stolen=st["stolen"], given=st["given"], idle_s=st["idle_s"],
+                                        pairs_local=len(mine))
 
     def set_theta(self, theta):
         self.theta = np.asarray(theta, dtype=np.float64).reshape(self.C, self.P).copy()
@@ -447,16 +571,58 @@ class ClusterGPEngine:
         return _lib.predict(self.Xs, self.offs, m["theta_dev"], m["W"], m["alpha_vec"], self.y_mean_dev, self.y_std_dev,
                             Qd, qlabel, self.kind, return_std, ws)
 
-    def ei_scan(self, Q, k=3, idx_base=0, want_arrays=False, qlabel=None, prune=False):
+    def ei_scan(self, Q, k=3, idx_base=0, want_arrays=False, qlabel=None, prune=False, penalty=None):
         """Dense EI scan of candidates Q -> ((score, idx, cluster) CUDA 1-elem tensors, arrays).
-        prune=True: exact bound-pruned scan, identical selection (see cgp_ei_argmax_pruned)."""
+        prune=True: exact bound-pruned scan, identical selection (see cgp_ei_argmax_pruned).
+        penalty: per-candidate additive soft-constraint term [M] (REF/cGP/acquisition.py:29) or None."""
         Qd = self._to_dev(Q)
         if qlabel is None:
             qlabel = self.route(Qd, k)
+        if penalty is not None:
+            penalty = self._to_dev(np.asarray(penalty, dtype=np.float64).reshape(-1) if not isinstance(penalty, torch.Tensor)
+                                   else penalty)
         m = self.model
         ws = self._workspace(_lib.score_workspace_bytes(self.offs, self.d, Qd.shape[0]))
         return _lib.ei_argmax(self.Xs, self.offs, m["theta_dev"], m["W"], m["alpha_vec"], self.y_mean_dev,
-                              self.y_std_dev, self.y_max_dev, Qd, qlabel, self.kind, idx_base, want_arrays, ws, prune)
+                              self.y_std_dev, self.y_max_dev, Qd, qlabel, self.kind, idx_base, want_arrays, ws, prune,
+                              penalty=penalty)
+
+    def penalty_of(self, Q, qlabel, boundary_penalty):
+        """Evaluate the reference's soft-constraint hook ``boundary_penalty(X, data_X)`` (REF/cGP/acquisition.py:29:
+        called per point with the samples of the point's cluster) for every candidate at once: per routed cluster one
+        vectorised call ``boundary_penalty(Q_c, X_c)``; hooks that only work point-wise are called per candidate.
+        -> [M] float64 CUDA tensor, or None when the hook returns 0 everywhere."""
+        Qh = Q.cpu().numpy() if isinstance(Q, torch.Tensor) else np.asarray(Q, dtype=np.float64)
+        ql = qlabel.cpu().numpy()
+        pen = np.zeros(Qh.shape[0])
+        for c in range(self.C):
+            sel = np.nonzero(ql == c)[0]
+            if not len(sel):
+                continue
+            Xc = self.X_host[self.labels_host == c]
+            v = None
+            try:
+                v = np.asarray(boundary_penalty(Qh[sel], Xc), dtype=np.float64)
+                if v.ndim == 0:
+                    v = np.full(len(sel), float(v))
+                v = v.reshape(-1)
+                if v.shape[0] != len(sel):
+                    v = None
+                else:  # spot-check the vectorised call against the reference's point-wise convention
+                    for j in sel[:: max(1, len(sel) // 4)][:4]:
+                        pj = float(np.asarray(boundary_penalty(Qh[j].reshape(1, -1), Xc), dtype=np.float64).reshape(-1)[0])
+                        if not np.isclose(pj, v[np.nonzero(sel == j)[0][0]], rtol=1e-12, atol=0.0):
+                            v = None
+                            break
+            except Exception:  # noqa: BLE001  (hook written for one point only)
+                v = None
+            if v is None:
+                v = np.array([float(np.asarray(boundary_penalty(Qh[j].reshape(1, -1), Xc), dtype=np.float64).reshape(-1)[0])
+                              for j in sel])
+            pen[sel] = v
+        if not np.any(pen):
+            return None
+        return torch.from_numpy(pen).to(self.device)
 
     # ------------------------------------------------------------------ MSPE (the reference's second acquisition)
     def _mspe_factors(self, c):
@@ -527,14 +693,16 @@ class ClusterGPEngine:
             arr[perm] = -neg_sorted
         return (-best[0], best[1], best[2]), arr
 
-    def select_next(self, candidates, k=3, sharded=False, prune=True):
+    def select_next(self, candidates, k=3, sharded=False, prune=True, boundary_penalty=None):
         """Pick the next sample from `candidates` [M,d].
 
         sharded=False: `candidates` is the full array (identical on every rank); each rank scores its
         contiguous shard.  sharded=True: `candidates` is already this rank's shard and idx_base is derived
         from the shard sizes (all-gathered).  Returns (x_next np[d], score, global idx, cluster).
         prune=True (default): the exact bound-pruned scan (cgp_ei_argmax_pruned) — same selected candidate and the same
-        score bits as the exhaustive scan (tests/test_gpu_prune.py); prune=False scores every candidate."""
+        score bits as the exhaustive scan (tests/test_gpu_prune.py); prune=False scores every candidate.
+        boundary_penalty: the reference's soft-constraint hook (X, data_X) -> additive term (see penalty_of); it is added
+        to EI inside the GPU score, (EI + penalty) / n_c."""
         rank, ws = cdist.world()
         if sharded:
             local = self._to_dev(candidates)
@@ -550,7 +718,9 @@ class ClusterGPEngine:
             lo, hi = cdist.shard_range(M, rank, ws)
             local = self._to_dev(candidates[lo:hi])
             base = lo
-        (bs, bi, bc), _ = self.ei_scan(local, k, idx_base=base, prune=prune)
+        ql = self.route(local, k)
+        pen = None if boundary_penalty is None else self.penalty_of(local, ql, boundary_penalty)
+        (bs, bi, bc), _ = self.ei_scan(local, k, idx_base=base, prune=prune, qlabel=ql, penalty=pen)
         li = int(bi.item()) - base
         x_local = local[li] if li >= 0 else torch.zeros(self.d, dtype=torch.float64, device=self.device)
         score, idx, cl, x, _owner = cdist.reduce_best(bs, bi, bc, x_local, rank, ws)

@@ -43,7 +43,7 @@ class _Run:
     """One L-BFGS-B state machine (the body of _minimize_lbfgsb's while-loop, turned inside out)."""
 
     __slots__ = ("x", "f", "g", "lo", "hi", "nbd", "wa", "iwa", "task", "ln_task", "lsave", "isave", "dsave", "m",
-                 "factr", "pgtol", "maxls", "maxiter", "maxfun", "nit", "nfev", "done", "best_f", "best_x")
+                 "factr", "pgtol", "maxls", "maxiter", "maxfun", "nit", "nfev", "done", "best_f", "best_x", "gid")
 
     def __init__(self, x0, lo, hi, m=10, ftol=2.2204460492503131e-09, gtol=1e-5, maxfun=15000, maxiter=15000,
                  maxls=20):
@@ -72,6 +72,7 @@ class _Run:
         self.done = False
         self.best_f = np.inf   # best evaluated point so far: the result of a run cut off by max_steps
         self.best_x = self.x.copy()
+        self.gid = -1          # global run id (minimize_async: runs migrate between ranks)
 
     def advance(self):
         """Run setulb until it asks for (f, g) at self.x (returns True) or terminates (returns False)."""
@@ -175,3 +176,196 @@ def minimize_lockstep(eval_batch, x0s, lo, hi, max_steps=100000, submit=None, co
     xs = np.stack([r.x if r.done else r.best_x for r in runs])
     fs = np.array([float(r.f) if r.done else float(r.best_f) for r in runs])
     return xs, fs, np.array([r.nfev for r in runs]), np.array([r.nit for r in runs]), steps
+
+
+# ======================================================================================================================
+# Asynchronous form: no global lock-step, several evaluation lanes per rank, work stealing between ranks
+# ======================================================================================================================
+class StealBoard:
+    """Work stealing between ranks over the c10d key-value store (the TCPStore every torch.distributed job already has).
+
+    Every rank owns whole L-BFGS-B runs and advances them without waiting for any other rank.  A rank whose number of
+    active runs falls two or more below the busiest rank's posts a request to that rank; the victim answers at its next
+    step boundary with the pickled state machines of some of its READY runs (an L-BFGS-B machine is ~15 KB), which
+    then continue on the thief.  A run's sequence of (theta -> f, g) evaluations does not depend on where or in which
+    batch it is evaluated (the kernels are batch-invariant bit for bit), so the result is independent of the schedule.
+    Nobody leaves the loop before all runs of all ranks are finished (global counter), so every request is answered.
+
+    Keys (under a per-fit prefix): load/<r> counter = active runs of rank r; done counter = finished runs (global);
+    req/<v> counter = requests posted to victim v; who/<v>/<k> = "<thief>:<thief load>"; give/<v>/<k> = pickled runs."""
+
+    def __init__(self, store, prefix, rank, world, total_runs):
+        self.store, self.prefix, self.rank, self.world, self.total = store, prefix, rank, world, total_runs
+        self._load = 0
+        self._served = 0
+        self._pending = None  # (victim, k) of the one request in flight
+        self.stolen = 0
+        self.given = 0
+
+    def _k(self, name):
+        return f"{self.prefix}/{name}"
+
+    def set_load(self, n):
+        if n != self._load:
+            self.store.add(self._k(f"load/{self.rank}"), n - self._load)
+            self._load = n
+
+    def add_done(self, k):
+        if k:
+            self.store.add(self._k("done"), k)
+
+    def all_done(self):
+        return self.store.add(self._k("done"), 0) >= self.total
+
+    def maybe_request(self, my_load):
+        """Post a request to the busiest rank if it holds at least two runs more than this rank."""
+        if self._pending is not None:
+            return
+        loads = [self.store.add(self._k(f"load/{r}"), 0) if r != self.rank else -1 for r in range(self.world)]
+        v = int(np.argmax(loads))
+        if loads[v] < my_load + 2:
+            return
+        k = self.store.add(self._k(f"req/{v}"), 1)
+        self.store.set(self._k(f"who/{v}/{k}"), f"{self.rank}:{my_load}")
+        self._pending = (v, k)
+
+    def poll_reply(self):
+        """-> list of stolen runs (possibly empty) when the pending request has been answered, else None."""
+        if self._pending is None:
+            return None
+        v, k = self._pending
+        key = self._k(f"give/{v}/{k}")
+        if not self.store.check([key]):
+            return None
+        import pickle
+
+        runs = pickle.loads(self.store.get(key))
+        self._pending = None
+        self.stolen += len(runs)
+        return runs
+
+    def serve(self, ready, my_total):
+        """Victim side, called at a step boundary: answer every new request out of `ready` (list of runs, mutated)."""
+        cnt = self.store.add(self._k(f"req/{self.rank}"), 0)
+        while self._served < cnt:
+            self._served += 1
+            import pickle
+
+            who = self.store.get(self._k(f"who/{self.rank}/{self._served}")).decode()
+            thief_load = int(who.split(":")[1])
+            give = max(0, min(len(ready), (my_total - thief_load) // 2))
+            out = [ready.pop() for _ in range(give)]
+            my_total -= give
+            self.given += give
+            self.store.set(self._k(f"give/{self.rank}/{self._served}"), pickle.dumps(out, protocol=pickle.HIGHEST_PROTOCOL))
+        return my_total
+
+
+def minimize_async(x0s, gids, lo, hi, submit, done, collect, n_lanes=2, lane_policy=None, board=None, max_evals=None,
+                   poll_sleep=50e-6):
+    """Minimise the runs this rank starts with (x0s[i] has global id gids[i]); with a StealBoard runs migrate between
+    ranks.  Evaluation interface (asynchronous, per lane):
+        ticket = submit(lane, gid [b] int64, X [b, n])   enqueue the evaluation of runs `gid` at `X` on lane `lane`
+        done(ticket) -> bool                             non-blocking
+        collect(ticket) -> (f [b], g [b, n])             blocks until finished
+    Every lane is an independent lock-step over the runs it currently holds; lanes are refilled from the pool of ready
+    runs as soon as they are free, so the device always has the next batch queued while the host advances the state
+    machines of the previous one, and the latency-bound part of one lane's factorisations overlaps the bulk of another's.
+    lane_policy(n_active) -> number of lanes to use at the moment (default: always n_lanes).
+    max_evals: stop every run after that many evaluations (it returns its best evaluated point).
+    Returns (results {gid: (x, f, nfev, nit)} of the runs that FINISHED on this rank, stats dict)."""
+    import time
+
+    runs_ready = []
+    finished = {}
+    n_steps = 0
+    n_evals = 0
+
+    def retire(r):
+        if r.done:
+            finished[r.gid] = (r.x.copy(), float(r.f), r.nfev, r.nit)
+        else:
+            finished[r.gid] = (r.best_x.copy(), float(r.best_f), r.nfev, r.nit)
+
+    new_done = 0
+    for x0, gid in zip(x0s, gids):
+        r = _Run(np.asarray(x0), lo, hi)
+        r.gid = int(gid)
+        if r.advance():
+            runs_ready.append(r)
+        else:
+            retire(r)
+            new_done += 1
+    lanes = [None] * n_lanes  # per lane: (ticket, [runs]) while busy
+    if board is not None:
+        board.set_load(len(runs_ready))
+        board.add_done(new_done)
+    t_idle = 0.0
+    while True:
+        progressed = False
+        in_flight = sum(len(l[1]) for l in lanes if l is not None)
+        # ---- absorb finished lanes
+        for li in range(n_lanes):
+            if lanes[li] is None or not done(lanes[li][0]):
+                continue
+            ticket, batch = lanes[li]
+            f, g = collect(ticket)
+            lanes[li] = None
+            n_steps += 1
+            new_done = 0
+            for k, r in enumerate(batch):
+                r.feed(f[k], g[k])
+                if max_evals is not None and r.nfev >= max_evals:
+                    retire(r)
+                    new_done += 1
+                elif r.advance():
+                    runs_ready.append(r)
+                else:
+                    retire(r)
+                    new_done += 1
+            in_flight -= len(batch)
+            progressed = True
+            if board is not None:
+                board.add_done(new_done)
+        # ---- work stealing: answer requests out of the ready pool, collect a reply, ask when short of work
+        if board is not None:
+            total = board.serve(runs_ready, len(runs_ready) + in_flight) if runs_ready else len(runs_ready) + in_flight
+            got = board.poll_reply()
+            if got:
+                runs_ready.extend(got)
+                total += len(got)
+                progressed = True
+            board.set_load(total)
+            if progressed or total == 0:
+                board.maybe_request(total)
+        # ---- refill free lanes from the ready pool
+        if runs_ready:
+            active = len(runs_ready) + in_flight
+            use = n_lanes if lane_policy is None else max(1, min(n_lanes, lane_policy(active)))
+            busy = sum(1 for l in lanes if l is not None)
+            free = [li for li in range(n_lanes) if lanes[li] is None][:max(0, use - busy)]
+            if free:
+                per = -(-len(runs_ready) // len(free))
+                for li in free:
+                    batch, runs_ready = runs_ready[:per], runs_ready[per:]
+                    if not batch:
+                        break
+                    gid = np.asarray([r.gid for r in batch], dtype=np.int64)
+                    X = np.stack([r.x.copy() for r in batch])
+                    n_evals += len(batch)
+                    lanes[li] = (submit(li, gid, X), batch)
+                    progressed = True
+        # ---- termination
+        if not runs_ready and all(l is None for l in lanes):
+            if board is None:
+                break
+            if board.all_done():
+                break
+            if board.serve([], 0):  # pragma: no cover  (serve returns the remaining total: 0)
+                pass
+        if not progressed:
+            t0 = time.perf_counter()
+            time.sleep(poll_sleep)
+            t_idle += time.perf_counter() - t0
+    return finished, dict(steps=n_steps, evals=n_evals, idle_s=t_idle,
+                          stolen=0 if board is None else board.stolen, given=0 if board is None else board.given)

@@ -44,6 +44,17 @@ int cgp_version(void);
 int cgp_create(cgp_handle** out, int device);
 int cgp_destroy(cgp_handle* h);
 
+/* Runtime switches of a handle (defaults come from the environment variables CGP_KNN_MODE = exact|tc,
+ * CGP_FORK_MAX, CGP_TILE_MODE = big|small at cgp_create).  None of them changes a result bit:
+ *   CGP_OPT_KNN_MODE   0 choose by problem size, 1 exact fp64 brute-force kernel only, 2 tensor-core prefilter + exact
+ *                      finish whenever k <= 3 (cgp_knn_labels)
+ *   CGP_OPT_FORK_MAX   batches of more matrices than this run the factorisation on ONE stream instead of the
+ *                      three-stream look-ahead schedule (0: never fork; measurement passes use it for exclusive timing)
+ *   CGP_OPT_TILE_MODE  0 CTA tile shape by launch size, 1 always 128x128, 2 always the small shapes */
+enum { CGP_OPT_KNN_MODE = 1, CGP_OPT_FORK_MAX = 2, CGP_OPT_TILE_MODE = 3 };
+int cgp_set_option(cgp_handle* h, int option, int value);
+int cgp_get_option(cgp_handle* h, int option, int* value);
+
 /* npad for a cluster of n samples. */
 int64_t cgp_padded_n(int64_t n);
 /* sum_c npad_c^2 — element count of the L / W factor buffers. */
@@ -110,14 +121,16 @@ int cgp_predict(cgp_handle* h, int kind, const double* X, const int64_t* offs_ho
  * by a dense scan of m candidates:
  *   score_i = EI(mean_i, std_i; y_max[c]) / n_c   with c = qlabel[i]
  *   best = argmax score; ties -> lowest cluster id, then lowest candidate index.
+ * penalty [m] (device, candidate order, NULL = none): the additive soft-constraint term of REF/cGP/acquisition.py:29,
+ *   score_i = (EI_i + penalty_i) / n_c  (the caller evaluates its boundary_penalty(x_i, X_c) hook per candidate).
  * Outputs (device): best_score[1], best_idx[1] (index into Q, plus idx_base), best_cluster[1];
  * score/mean/std [m] optional (NULL to skip). */
 int cgp_ei_argmax(cgp_handle* h, int kind, const double* X, const int64_t* offs_host,
                   int n_clusters, int d, const double* theta, const double* W,
                   const double* alpha_vec, const double* y_mean, const double* y_std,
                   const double* y_max, const double* Q, const int64_t* qlabel, int64_t m,
-                  int64_t idx_base, double* score, double* mean, double* std, double* best_score,
-                  int64_t* best_idx, int64_t* best_cluster, void* workspace,
+                  int64_t idx_base, const double* penalty, double* score, double* mean, double* std,
+                  double* best_score, int64_t* best_idx, int64_t* best_cluster, void* workspace,
                   size_t workspace_bytes, void* stream);
 
 /* Same selection as cgp_ei_argmax (identical best_score bits, best_idx, best_cluster) with exact bound pruning:
@@ -128,7 +141,7 @@ int cgp_ei_argmax_pruned(cgp_handle* h, int kind, const double* X, const int64_t
                          int n_clusters, int d, const double* theta, const double* W,
                          const double* alpha_vec, const double* y_mean, const double* y_std,
                          const double* y_max, const double* Q, const int64_t* qlabel, int64_t m,
-                         int64_t idx_base, double* best_score, int64_t* best_idx,
+                         int64_t idx_base, const double* penalty, double* best_score, int64_t* best_idx,
                          int64_t* best_cluster, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Incremental refit.  The reference re-clusters and re-factorises everything after
@@ -183,6 +196,9 @@ int cgp_profile_read(cgp_handle* h, double* ms, int64_t* launches, int n_cls, in
  * three-stream look-ahead schedule: their launches are counted but never timed (a bracket there would include work of
  * the other two streams); larger batches run on one stream, so ms / flops describe exclusive kernel time. */
 int cgp_profile_flops(cgp_handle* h, double* flops, int64_t* timed, int n_cls);
+/* on != 0: count but do not time the following launches of this handle (the caller is running a batch of ANOTHER handle
+ * concurrently on the same device, so event brackets would not be exclusive). */
+int cgp_profile_mute(cgp_handle* h, int on);
 
 #ifdef __cplusplus
 }

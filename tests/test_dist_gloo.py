@@ -70,7 +70,32 @@ def _worker(rank, world, port, q):
         sh = minimize_lockstep(fg, x0, lo3, hi3, shard=dict(rank=rank, world=world, cost=np.arange(n_runs) % 3 + 1.0,
                                                             allreduce=allreduce))
         ok_bal = all(np.array_equal(a, b) for a, b in zip(plain[:4], sh[:4])) and calls[0] < 0.7 * total_plain
-        q.put((rank, ok_fit, ok_sel and ok_bal, (lo, hi)))
+        # ---- asynchronous runs with work stealing over the c10d store: rank 0 starts with ALL runs, rank 1 with none
+        import time
+
+        from torch.distributed.distributed_c10d import _get_default_store
+
+        from cgp_b200.lbfgs import StealBoard, minimize_async
+
+        board = StealBoard(_get_default_store(), "test/fit1", rank, world, n_runs)
+        gids = np.arange(n_runs) if rank == 0 else np.arange(0)
+        fin, st = minimize_async([x0[i] for i in gids], gids, lo3, hi3,
+                                 lambda lane, gid, X: (time.perf_counter() + 3e-3, fg(gid, X)),
+                                 lambda t: time.perf_counter() >= t[0], lambda t: t[1], n_lanes=2, board=board)
+        table = np.zeros((n_runs, dim + 3))
+        for gid, (x, f, nfev, nit) in fin.items():
+            table[gid] = np.concatenate([x, [f, nfev, nit]])
+        t = torch.from_numpy(table)
+        dist.all_reduce(t)
+        counts = torch.tensor([float(len(fin)), float(st["stolen"]), float(st["given"])])
+        allc = [torch.zeros(3) for _ in range(world)]
+        dist.all_gather(allc, counts)
+        tot = t.numpy()
+        ok_async = (np.array_equal(tot[:, :dim], plain[0]) and np.array_equal(tot[:, dim], plain[1])
+                    and np.array_equal(tot[:, dim + 1], plain[2]) and np.array_equal(tot[:, dim + 2], plain[3])
+                    and sum(int(c[0]) for c in allc) == n_runs          # every run finished exactly once
+                    and int(allc[1][1]) > 0 and int(allc[0][2]) == int(allc[1][1]))  # rank 1 stole what rank 0 gave
+        q.put((rank, ok_fit, ok_sel and ok_bal and ok_async, (lo, hi)))
     finally:
         dist.destroy_process_group()
 

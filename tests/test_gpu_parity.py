@@ -142,15 +142,50 @@ def test_factorize_properties_large(lib):
 
 
 # ------------------------------------------------------------------------------------------------ K7
+@pytest.fixture(params=["exact", "tc"])
+def knn_mode(request, lib):
+    """Both k-NN paths: the exact fp64 brute-force kernel and the tensor-core prefilter + exact finish (forced on even
+    for training sets it would not normally be chosen for)."""
+    old = lib.set_option("knn_mode", request.param)
+    yield request.param
+    lib.set_option("knn_mode", old)
+
+
 @pytest.mark.parametrize("name", ["fit_select_d2", "fit_select_d6"])
-def test_knn_bit_exact_vs_sklearn(lib, name):
+def test_knn_bit_exact_vs_sklearn(lib, name, knn_mode):
     g = load_golden(name)
     C = int(g["labels"].max()) + 1
     lab = lib.knn_labels(dev(g["X"]), dev(g["labels"], torch.int64), dev(g["Q"]), 3, C).cpu().numpy()
     assert np.array_equal(lab, g["qlab"])
 
 
-def test_knn_ties_and_k(lib):
+@pytest.mark.parametrize("d,n,m,k", [(8, 8192, 20000, 3), (6, 5000, 12000, 3), (11, 3000, 6000, 2), (2, 4000, 9000, 1),
+                                     (16, 2100, 4100, 3)])
+def test_knn_prefilter_bit_exact_random(lib, knn_mode, d, n, m, k):
+    """Continuous data (the prefilter certifies almost every query) incl. near-duplicates of training points."""
+    rng = np.random.default_rng(100 + d)
+    X = rng.uniform(size=(n, d))
+    labels = rng.integers(0, 9, size=n)
+    Q = rng.uniform(size=(m, d))
+    Q[: m // 8] = X[rng.integers(0, n, size=m // 8)] + 1e-9 * rng.standard_normal((m // 8, d))
+    Q[m // 8: m // 6] = X[rng.integers(0, n, size=m // 6 - m // 8)]  # exact copies of training points
+    got = lib.knn_labels(dev(X), dev(labels, torch.int64), dev(Q), k, 9).cpu().numpy()
+    assert np.array_equal(got, oracle.knn_labels(X, labels, Q, k))
+
+
+def test_knn_prefilter_offset_and_scaled_data(lib, knn_mode):
+    """Coordinates far from the origin (the error bound of the fp32 ranking grows with |x|^2: most queries fall back
+    to the exact kernel) and Schaffer-like [-100, 100] boxes: labels stay bit-exact."""
+    rng = np.random.default_rng(77)
+    for shift, scale in ((1000.0, 1.0), (0.0, 100.0), (-3.0e4, 10.0)):
+        X = shift + scale * rng.uniform(-1, 1, size=(3000, 3))
+        labels = rng.integers(0, 4, size=3000)
+        Q = shift + scale * rng.uniform(-1, 1, size=(5000, 3))
+        got = lib.knn_labels(dev(X), dev(labels, torch.int64), dev(Q), 3, 4).cpu().numpy()
+        assert np.array_equal(got, oracle.knn_labels(X, labels, Q, 3))
+
+
+def test_knn_ties_and_k(lib, knn_mode):
     """Integer grid -> many exact distance ties; lowest training index must win, vote ties -> smallest label."""
     rng = np.random.default_rng(9)
     X = rng.integers(0, 4, size=(600, 3)).astype(np.float64)

@@ -1,6 +1,7 @@
 """CPU: host-side logic — lock-step L-BFGS-B equals scipy.optimize.minimize bit for bit, restart draws equal
 scikit-learn's, kernel parsing, plugin contracts."""
 import numpy as np
+import pytest
 import scipy.optimize
 
 import oracle
@@ -116,3 +117,61 @@ def test_pipelined_lockstep_equals_plain():
     assert np.array_equal(plain[0], piped[0]) and np.array_equal(plain[1], piped[1])
     assert np.array_equal(plain[2], piped[2]) and np.array_equal(plain[3], piped[3])
     assert not tickets
+
+
+def _toy_problem(n_runs=23, dim=4, seed=5):
+    rng = np.random.default_rng(seed)
+    A = rng.uniform(0.5, 2.0, size=(n_runs, dim))
+    c = rng.uniform(-1, 1, size=(n_runs, dim))
+
+    def fg(idx, Xs):
+        r = Xs - c[idx]
+        return (A[idx] * r ** 2).sum(1) + 0.1 * np.sin(3 * Xs).sum(1), 2 * A[idx] * r + 0.3 * np.cos(3 * Xs)
+
+    x0 = [rng.uniform(-2, 2, size=dim) for _ in range(n_runs)]
+    return fg, x0, np.full(dim, -3.0), np.full(dim, 3.0)
+
+
+@pytest.mark.parametrize("n_lanes,policy", [(1, None), (2, None), (3, None), (2, lambda a: 2 if a <= 6 or a > 15 else 1)])
+def test_async_lanes_equal_lockstep(n_lanes, policy):
+    """minimize_async (independent evaluation lanes, no lock-step) gives every run exactly the result of the lock-step
+    driver / scipy.optimize.minimize: a run's evaluation sequence does not depend on the batching."""
+    import time
+
+    from cgp_b200.lbfgs import minimize_async
+
+    fg, x0, lo, hi = _toy_problem()
+    plain = minimize_lockstep(fg, x0, lo, hi)
+    in_flight = [0]
+    max_in_flight = [0]
+
+    def submit(lane, gid, X):
+        in_flight[0] += 1
+        max_in_flight[0] = max(max_in_flight[0], in_flight[0])
+        return (time.perf_counter() + 2e-4 * (1 + lane), fg(gid, X))
+
+    def collect(t):
+        in_flight[0] -= 1
+        return t[1]
+
+    fin, st = minimize_async(x0, np.arange(len(x0)), lo, hi, submit, lambda t: time.perf_counter() >= t[0], collect,
+                             n_lanes=n_lanes, lane_policy=policy)
+    assert sorted(fin) == list(range(len(x0)))
+    for i in range(len(x0)):
+        x, f, nfev, nit = fin[i]
+        assert np.array_equal(x, plain[0][i]) and f == plain[1][i] and nfev == plain[2][i] and nit == plain[3][i]
+    assert st["evals"] == plain[2].sum() and max_in_flight[0] <= n_lanes
+    if n_lanes > 1 and policy is None:
+        assert max_in_flight[0] == n_lanes
+
+
+def test_async_max_evals_keeps_best_evaluated_point():
+    from cgp_b200.lbfgs import minimize_async
+
+    fg, x0, lo, hi = _toy_problem(5)
+    fin, st = minimize_async(x0, np.arange(5), lo, hi, lambda lane, gid, X: fg(gid, X), lambda t: True, lambda t: t,
+                             n_lanes=2, max_evals=1)
+    f0, _ = fg(np.arange(5), np.stack(x0))
+    for i in range(5):
+        assert np.array_equal(fin[i][0], x0[i]) and fin[i][1] == f0[i] and fin[i][2] == 1
+    assert st["evals"] == 5
