@@ -353,6 +353,7 @@ def run_b200(args, preset):
     stats = {}
 
     def step(q_src, from_host, prune=True):
+        stats.pop("_model", None)  # the previous step's model (configs[3]: 69 GB of factors) is released first
         e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
         e[0].record()
         q = q_src.to(dev, non_blocking=True) if from_host else q_src
@@ -369,7 +370,9 @@ def run_b200(args, preset):
                      lockstep=fs["lockstep"], eval_s=fs["eval_s"], opt_host_s=fs["optimizer_host_s"],
                      evals_per_cluster=fs["evals_per_cluster"].tolist(), nfev_sorted=sorted(int(v) for v in fs["nfev"]),
                      x_next=x_next.tolist(), score=score, idx=idx, sizes=eng.counts.tolist(),
-                     lml=eng.model["lml_host"].tolist(), shard_mode=fs["shard_mode"])
+                     lml=eng.model["lml_host"].tolist(), shard_mode=fs["shard_mode"],
+                     fit_async={k: (round(v, 4) if isinstance(v, float) else v) for k, v in fs.items()
+                                if k in ("lanes", "stolen", "given", "idle_s", "pairs_local")})
         stats["_model"] = model
         return x_next
 
@@ -501,7 +504,7 @@ def run_b200(args, preset):
             "gpu_launches": gpu_launches, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
             "acq": "exact bound-pruned scan (public default)", "acq_exhaustive_scan": exhaustive,
             "acq_candidates_per_s": M / res["acq_s"], "lml_evals_per_fit_rank0": res["evals"],
-            "lml_evals_committed": evals_file, "lockstep_per_fit": res["lockstep"], "shard_mode": res["shard_mode"],
+            "lml_evals_committed": evals_file, "lockstep_per_fit": res["lockstep"], "shard_mode": res["shard_mode"], "fit_async_rank0": res["fit_async"],
             "fit_eval_wall_s": round(res["eval_s"], 4), "fit_optimizer_host_s": round(res["opt_host_s"], 4),
             "wall_s_per_step": t_wall / args.steps,
             "parallelism": f"(cluster, restart) runs + candidates sharded over {world} GPU(s)",

@@ -46,6 +46,9 @@ SIGNATURES = {
     "cgp_append_workspace_bytes": (_sz, [_i64]),
     "cgp_append_sample": (C.c_int, [_vp, C.c_int, _vp, _i64, C.c_int, _vp, _f64, _vp, _vp, _i64, _vp, _vp, _sz, _vp]),
     "cgp_refresh_alpha": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "cgp_quadform_workspace_bytes": (_sz, [_pi64, C.c_int, C.c_int, _i64]),
+    "cgp_quadform_scan": (C.c_int, [_vp, C.c_int, _vp, _pi64, C.c_int, C.c_int, _vp, _vp, C.POINTER(C.c_double), _vp, _vp, _i64,
+                                    _i64, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "cgp_rowdot": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp]),
     "cgp_argmax_sorted": (C.c_int, [_vp, _vp, _i64, _vp, _vp, C.c_int, _i64, _vp, _vp, _vp, _vp, _sz, _vp]),
     "cgp_dgemm_nt": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp]),
@@ -271,6 +274,32 @@ def argmax_sorted(score_sorted, perm, coff, idx_base=0):
                                  _ptr(bc, torch.int64), _ptr(scratch, torch.uint8), scratch.numel(), _stream(dev)),
          "cgp_argmax_sorted")
     return bs, bi, bc
+
+
+def quadform_workspace_bytes(offs, d, m):
+    o, po = _host_i64(offs)
+    return int(lib().cgp_quadform_workspace_bytes(po, len(o) - 1, d, int(m)))
+
+
+def quadform_scan(X, offs, theta, Bmat, c0, Q, qlabel, kind, idx_base=0, penalty=None, want_values=False, workspace=None):
+    """Dense MSPE scan (cgp_quadform_scan) -> ((min value, idx, cluster) 1-element CUDA tensors, values [m] | None)."""
+    o, po = _host_i64(offs)
+    d = X.shape[1]
+    m = Q.shape[0]
+    dev = X.device
+    bs = torch.empty(1, dtype=torch.float64, device=dev)
+    bi = torch.empty(1, dtype=torch.int64, device=dev)
+    bc = torch.empty(1, dtype=torch.int64, device=dev)
+    val = torch.empty(m, dtype=torch.float64, device=dev) if want_values else None
+    if workspace is None:
+        workspace = torch.empty(quadform_workspace_bytes(o, d, m), dtype=torch.uint8, device=dev)
+    c0 = np.ascontiguousarray(c0, dtype=np.float64)
+    _chk(lib().cgp_quadform_scan(handle(dev.index), KIND[kind], _ptr(X), po, len(o) - 1, d, _ptr(theta), _ptr(Bmat),
+                                 c0.ctypes.data_as(C.POINTER(C.c_double)), _ptr(Q), _ptr(qlabel, torch.int64), m,
+                                 int(idx_base), _ptr(penalty), _ptr(val), _ptr(bs), _ptr(bi, torch.int64),
+                                 _ptr(bc, torch.int64), _ptr(workspace, torch.uint8), workspace.numel(), _stream(dev)),
+         "cgp_quadform_scan")
+    return (-bs, bi, bc), val
 
 
 def knn_labels(X, labels, Q, k, n_classes):

@@ -99,14 +99,12 @@ class CGPRegressor:
                                                       boundary_penalty=boundary_penalty)
         return x, score, idx
 
-    def select_next_mspe(self, candidates):
+    def select_next_mspe(self, candidates, sharded=False, boundary_penalty=None):
         """Dense scan of the reference's second acquisition (REF/cGP/acquisition.py:34-75, minimised):
-        -> (x_next [d], mspe / n_c, idx).  Single rank."""
-        eng = self.engine_
-        Q = eng._to_dev(candidates)
-        (v, i, _c), _ = eng.mspe_scan(Q, self.n_neighbors)
-        idx = int(i.item())
-        return Q[idx].cpu().numpy(), float(v.item()), idx
+        -> (x_next [d], (mspe + penalty) / n_c, idx).  Multi-GPU aware like select_next."""
+        x, v, idx, _cl = self.engine_.select_next_mspe(candidates, self.n_neighbors, sharded=sharded,
+                                                        boundary_penalty=boundary_penalty)
+        return x, v, idx
 
     def mspe_candidates(self, candidates):
         """mspe / n_c of every candidate (host array), the batched form of acquisition.mean_square_prediction_error."""

@@ -58,6 +58,9 @@ struct HandleImpl : cgp_handle {
     long long timed[CLS_COUNT];    // launches that were bracketed by events
     void* knn_buf;     // scratch of the tensor-core k-NN prefilter (grow-only)
     size_t knn_bytes;
+    long long* knn_qlist;  // list / count of the queries the last prefilter launch could not certify (inside knn_buf)
+    int* knn_qcount;
+    int knn_qcap;
     int knn_mode;      // 0 = by problem size, 1 = always the exact fp64 kernel, 2 = prefilter whenever k <= 3 (CGP_KNN_MODE)
     int fork_max;  // batches with more matrices than this run the one-stream schedule (CGP_FORK_MAX, default 24)
     // internal streams of run_pipeline: sc (high priority) = the dependent chain update -> diag -> panel + look-ahead part
@@ -863,7 +866,9 @@ static int launch_knn_tc(HandleImpl* h, const double* X, const long long* lab, i
                          long long* out, cudaStream_t s) {
     const int npad = (n + KTC_TILE - 1) / KTC_TILE * KTC_TILE;
     const size_t o_xn = align_up((size_t)npad * DP * 8, 256), o_st = align_up(o_xn + (size_t)npad * 4, 256);
-    const size_t need = o_st + (DP + 1) * 4;
+    const int qcap = (int)std::min<long long>(M, 1 << 20);  // listed uncertified queries (more only carry the -1 mark)
+    const size_t o_cnt = align_up(o_st + (DP + 1) * 4, 256), o_list = o_cnt + 256;
+    const size_t need = o_list + (size_t)qcap * 8;
     if (need > h->knn_bytes) {  // grow-only scratch of the handle (split training set, norms, statistics)
         CGP_CHECK(cudaStreamSynchronize(s));
         if (h->knn_buf) CGP_CHECK(cudaFree(h->knn_buf));
@@ -876,12 +881,18 @@ static int launch_knn_tc(HandleImpl* h, const double* X, const long long* lab, i
     float2* Xp = reinterpret_cast<float2*>(buf);
     float* xn = reinterpret_cast<float*>(buf + o_xn);
     float* stats = reinterpret_cast<float*>(buf + o_st);
+    int* qcount = reinterpret_cast<int*>(buf + o_cnt);
+    long long* qlist = reinterpret_cast<long long*>(buf + o_list);
+    CGP_CHECK(cudaMemsetAsync(qcount, 0, sizeof(int), s));
     KL(h, CLS_KNN_PREP, s, k_knn_prep<DP><<<(unsigned)((npad + 255) / 256), 256, 0, s>>>(X, n, npad, d, Xp, xn));
     KL(h, CLS_KNN_PREP, s, k_knn_stats<DP><<<1, 1024, 0, s>>>(X, n, d, stats));
     const int sm = KTC_SMEM_BYTES(DP);
     CGP_CHECK(cudaFuncSetAttribute(k_knn_tc<DP>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
     KL(h, CLS_KNN, s, k_knn_tc<DP><<<(unsigned)((M + KTC_QPB - 1) / KTC_QPB), 256, sm, s>>>(Xp, xn, stats, X, lab, n, npad, d, k, Q,
-                                                                                           M, out));
+                                                                                           M, out, qlist, qcount, qcap));
+    h->knn_qlist = qlist;
+    h->knn_qcount = qcount;
+    h->knn_qcap = qcap;
     return (int)cudaGetLastError();
 }
 
@@ -900,11 +911,15 @@ static int launch_knn(HandleImpl* h, const double* X, const long long* lab, int 
     if (tc) {
         int rc = D <= 8 ? launch_knn_tc<8>(h, X, lab, n, D, k, Q, M, out, s) : launch_knn_tc<16>(h, X, lab, n, D, k, Q, M, out, s);
         if (rc) return rc;
-        // queries the prefilter could not certify (out = -1): exact brute force; blocks without one exit at once
-        KL(h, CLS_KNN_EXACT, s, k_knn<D><<<grid, KNN_THREADS, sm, s>>>(X, lab, n, k, Q, M, out, 1));
+        // queries the prefilter could not certify: exact brute force, dense over the list (blocks past the count exit),
+        // then a sweep for marks that did not fit the list (blocks without one exit at once)
+        const unsigned lgrid = (unsigned)((h->knn_qcap + KNN_THREADS - 1) / KNN_THREADS);
+        KL(h, CLS_KNN_EXACT, s, k_knn<D><<<lgrid, KNN_THREADS, sm, s>>>(X, lab, n, k, Q, M, out, 0, h->knn_qlist, h->knn_qcount,
+                                                                        h->knn_qcap));
+        KL(h, CLS_KNN_EXACT, s, k_knn<D><<<grid, KNN_THREADS, sm, s>>>(X, lab, n, k, Q, M, out, 1, nullptr, nullptr, 0));
         return (int)cudaGetLastError();
     }
-    KL(h, CLS_KNN_EXACT, s, k_knn<D><<<grid, KNN_THREADS, sm, s>>>(X, lab, n, k, Q, M, out, 0));
+    KL(h, CLS_KNN_EXACT, s, k_knn<D><<<grid, KNN_THREADS, sm, s>>>(X, lab, n, k, Q, M, out, 0, nullptr, nullptr, 0));
     return (int)cudaGetLastError();
 }
 
@@ -1145,6 +1160,90 @@ extern "C" int cgp_ei_argmax_pruned(cgp_handle* hh, int kind, const double* X, c
     return run_score(h, kind, X, offs, C, d, theta, W, alpha_vec, y_mean, y_std, y_max, Q, qlabel, m, idx_base, nullptr,
                      nullptr, nullptr, best_score, best_idx, best_cluster, workspace, ws_bytes, (cudaStream_t)stream, true,
                      penalty);
+}
+
+// ------------------------------------------------------------------------------------------------
+// dense MSPE scan: value_i = (c0[c] - k*_i^T B_c k*_i + penalty_i) / n_c, minimum wins
+// ------------------------------------------------------------------------------------------------
+extern "C" size_t cgp_quadform_workspace_bytes(const int64_t* offs, int C, int d, int64_t m) {
+    if (!offs || C <= 0 || m < 0) return 0;
+    ScoreLayout L = score_layout(offs, C, d, m);
+    return L.total + align_up((size_t)L.mch * L.npad_max * 8, 256);
+}
+
+extern "C" int cgp_quadform_scan(cgp_handle* hh, int kind, const double* X, const int64_t* offs, int C, int d,
+                                 const double* theta, const double* Bmat, const double* c0_host, const double* Q,
+                                 const int64_t* qlabel, int64_t m, int64_t idx_base, const double* penalty, double* value,
+                                 double* best_value, int64_t* best_idx, int64_t* best_cluster, void* workspace,
+                                 size_t ws_bytes, void* stream) {
+    CGP_ENTER(hh);
+    if (kind != 0 && kind != 1) return -2;
+    if (!X) return -3;
+    if (!offs || C <= 0 || C > 4096) return -4;
+    if (d < 1 || d > CGP_MAX_D) return -6;
+    if (!theta) return -7;
+    if (!Bmat) return -8;
+    if (!c0_host) return -9;
+    if (m <= 0) return -12;
+    if (!Q) return -10;
+    if (!qlabel) return -11;
+    if (!best_value) return -16;
+    if (!best_idx) return -17;
+    if (!best_cluster) return -18;
+    if (!workspace) return -19;
+    ScoreLayout L = score_layout(offs, C, d, m);
+    const size_t o_y = L.total;
+    if (o_y + align_up((size_t)L.mch * L.npad_max * 8, 256) > ws_bytes) return -100;
+    cudaStream_t s = (cudaStream_t)stream;
+    char* ws = static_cast<char*>(workspace);
+    long long* perm = reinterpret_cast<long long*>(ws + L.o_perm);
+    double* Qs = reinterpret_cast<double*>(ws + L.o_qs);
+    double* sorted = reinterpret_cast<double*>(ws + L.o_sorted);
+    int* hist = reinterpret_cast<int*>(ws + L.o_hist);
+    long long* blkoff = reinterpret_cast<long long*>(ws + L.o_blkoff);
+    long long* coff = reinterpret_cast<long long*>(ws + L.o_coff);
+    double* blkv = reinterpret_cast<double*>(ws + L.o_blkv);
+    long long* blkp = reinterpret_cast<long long*>(ws + L.o_blkp);
+    double* kstar = reinterpret_cast<double*>(ws + L.o_kstar);
+    double* qf = reinterpret_cast<double*>(ws + L.o_mraw);
+    double* Y = reinterpret_cast<double*>(ws + o_y);
+    const long long* ql = reinterpret_cast<const long long*>(qlabel);
+    KL(h, CLS_BUCKET, s, k_bucket_hist<<<L.nblk, 256, (size_t)C * 4, s>>>(ql, m, C, L.nblk, hist));
+    KL(h, CLS_BUCKET, s, k_bucket_scan<<<1, 1024, 0, s>>>(hist, blkoff, coff, C, L.nblk));
+    KL(h, CLS_BUCKET, s, k_bucket_scatter<<<L.nblk, 32, (size_t)C * 8, s>>>(ql, Q, m, C, L.nblk, d, blkoff, perm, Qs));
+    CGP_CHECK(cudaGetLastError());
+    std::vector<long long> hoff(C + 1);
+    CGP_CHECK(cudaMemcpyAsync(hoff.data(), coff, (size_t)(C + 1) * 8, cudaMemcpyDeviceToHost, s));
+    CGP_CHECK(cudaStreamSynchronize(s));
+    const int P = d + 1;
+    long long boff = 0;
+    for (int c = 0; c < C; ++c) {
+        const int64_t n = offs[c + 1] - offs[c];
+        const int64_t npad = pad_n(n);
+        const double* Bc = Bmat + boff;
+        boff += npad * npad;
+        const double* th = theta + (long long)c * P;
+        const double* Xc = X + offs[c] * d;
+        for (long long p0 = hoff[c]; p0 < hoff[c + 1]; p0 += L.mch) {
+            const long long rows = std::min<long long>(L.mch, hoff[c + 1] - p0);
+            const long long rows_pad = pad_n(rows);
+            int rc = launch_cross(h, kind, Qs + p0 * d, rows, Xc, n, d, th, kstar, npad, rows_pad, npad, 0, 0.0, s);
+            if (rc) return rc;
+            // Y = K* B  (B symmetric: K* B^T through the NT tile GEMM), q = rowdot(Y, K*)
+            FL(h, 2.0 * (double)rows * (double)n * (double)n);
+            KL(h, CLS_DGEMM, s, k_dgemm_nt<<<dim3((unsigned)(npad / CGP_TILE), (unsigned)(rows_pad / CGP_TILE)), CGP_GEMM_THREADS,
+                                             GEMM_SMEM_BYTES, s>>>(kstar, Bc, Y, rows_pad, npad, (int)npad));
+            KL(h, CLS_SCORE_FINISH, s, k_rowdot<<<(unsigned)((rows + 7) / 8), 256, 0, s>>>(Y, kstar, rows, (int)n, npad, qf));
+            KL(h, CLS_SCORE_FINISH, s, k_quadform_finish<<<(unsigned)((rows + 255) / 256), 256, 0, s>>>(
+                                           qf, rows, p0, perm, c0_host[c], (double)n, penalty, value, sorted));
+        }
+    }
+    int nb = (int)std::min<long long>(1024, (m + 255) / 256);
+    KL(h, CLS_ARGMAX, s, k_argmax_blocks<<<nb, 256, 0, s>>>(sorted, m, blkv, blkp));
+    KL(h, CLS_ARGMAX, s, k_argmax_final<<<1, 256, 0, s>>>(blkv, blkp, nb, perm, coff, C, idx_base, best_value,
+                                                          reinterpret_cast<long long*>(best_idx),
+                                                          reinterpret_cast<long long*>(best_cluster)));
+    return (int)cudaGetLastError();
 }
 
 extern "C" int cgp_rowdot(cgp_handle* hh, const double* A, const double* B, int64_t rows, int64_t n, int64_t ld, double* out,

@@ -12,15 +12,26 @@
 template <int D>
 __global__ void __launch_bounds__(KNN_THREADS)
 k_knn(const double* __restrict__ X, const long long* __restrict__ lab, int n, int k, const double* __restrict__ Q, long long M,
-      long long* __restrict__ out, int only_flagged) {
+      long long* __restrict__ out, int only_flagged, const long long* __restrict__ qlist, const int* __restrict__ qcount,
+      int qcap) {
     extern __shared__ __align__(16) double sm[];
     double* xs = sm;                                          // [KNN_TILE][D]
     int* ls = reinterpret_cast<int*>(sm + KNN_TILE * D);      // [KNN_TILE]
-    const long long q = (long long)blockIdx.x * KNN_THREADS + threadIdx.x;
-    // only_flagged: second pass behind the tensor-core prefilter (knn_tc.cuh): only queries it could not certify
-    // (out[q] == -1) are computed; blocks without one exit at once
-    const bool active = q < M && (!only_flagged || out[q] == -1);
-    if (only_flagged && !__syncthreads_or(active)) return;
+    // Passes behind the tensor-core prefilter (knn_tc.cuh), which marks the queries it could not certify with
+    // out[q] = -1 and appends them to qlist (up to qcap entries):
+    //   qlist != NULL   dense pass over the listed queries (thread i handles qlist[i]);
+    //   only_flagged    sweep over ALL queries for marks that did not fit the list; blocks without one exit at once.
+    long long q = (long long)blockIdx.x * KNN_THREADS + threadIdx.x;
+    bool active = q < M;
+    if (qlist) {
+        const int cnt = min(*qcount, qcap);
+        if ((long long)blockIdx.x * KNN_THREADS >= cnt) return;
+        active = q < cnt;
+        q = active ? qlist[q] : 0;
+    } else if (only_flagged) {
+        active = active && out[q] == -1;
+        if (!__syncthreads_or(active)) return;
+    }
     double qv[D];
 #pragma unroll
     for (int p = 0; p < D; ++p) qv[p] = active ? Q[q * D + p] : 0.0;

@@ -123,18 +123,22 @@ __device__ __forceinline__ void ktc_insert(float (&v)[KTC_KP], int (&ix)[KTC_KP]
 // ---- main kernel --------------------------------------------------------------------------------------------------
 // grid ceil(M / 128), block 256.  Dynamic smem: 2 stages x (KTC_TILE x DP float2 + KTC_TILE float) + merge area
 // 8 warps x 16 rows x 16 entries x (float + int).
-#define KTC_STAGE_BYTES(DP) (KTC_TILE * (DP) * 8 + KTC_TILE * 4)
+// Row stride of a training point in shared memory: DP + 4 float2.  The B fragment load of lane (g, t) reads the float2
+// at row g, slot t (and t + 4): with stride DP + 4 the 16 lanes of a half-warp hit (4 g + t) mod 16 = 16 different
+// 8-byte bank pairs (stride DP: 8 g + t -> 2-way conflicts, ncu: 4.4e9 conflicts for the 4M x 32k routing).
+#define KTC_LD(DP) ((DP) + 4)
+#define KTC_STAGE_BYTES(DP) (KTC_TILE * KTC_LD(DP) * 8 + KTC_TILE * 4)
 #define KTC_SMEM_BYTES(DP) (2 * KTC_STAGE_BYTES(DP) + 8 * 16 * 16 * 8)
 
 template <int DP>
 __device__ __forceinline__ void ktc_load_stage(char* stage, const float2* __restrict__ Xp, const float* __restrict__ xn, int t0,
                                                int tid) {
-    // KTC_TILE x DP float2 = KTC_TILE * DP * 8 bytes in 16-byte chunks, then the norms
-    constexpr int XCH = KTC_TILE * DP * 8 / 16;
+    // KTC_TILE rows of DP float2 (DP * 8 bytes = CPR 16-byte chunks each) at row stride KTC_LD(DP), then the norms
+    constexpr int CPR = DP * 8 / 16, XCH = KTC_TILE * CPR;
     const char* gx = reinterpret_cast<const char*>(Xp + (long long)t0 * DP);
-    for (int c = tid; c < XCH; c += 256) cp_async16(stage + c * 16, gx + c * 16);
+    for (int c = tid; c < XCH; c += 256) cp_async16(stage + (c / CPR) * (KTC_LD(DP) * 8) + (c % CPR) * 16, gx + c * 16);
     const char* gn = reinterpret_cast<const char*>(xn + t0);
-    char* sn = stage + KTC_TILE * DP * 8;
+    char* sn = stage + KTC_TILE * KTC_LD(DP) * 8;
     for (int c = tid; c < KTC_TILE * 4 / 16; c += 256) cp_async16(sn + c * 16, gn + c * 16);
 }
 
@@ -142,7 +146,8 @@ template <int DP>
 __global__ void __launch_bounds__(256)
 k_knn_tc(const float2* __restrict__ Xp, const float* __restrict__ xn, const float* __restrict__ stats,
          const double* __restrict__ X, const long long* __restrict__ lab, int n, int npad, int d, int k,
-         const double* __restrict__ Q, long long M, long long* __restrict__ out) {
+         const double* __restrict__ Q, long long M, long long* __restrict__ out, long long* __restrict__ qlist,
+         int* __restrict__ qcount, int qcap) {
     extern __shared__ __align__(16) char ktc_smem[];
     constexpr int KS = DP / 8;  // k-steps per tile
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -181,26 +186,31 @@ k_knn_tc(const float2* __restrict__ Xp, const float* __restrict__ xn, const floa
         __syncthreads();
         const char* stage = ktc_smem + (tl & 1) * KTC_STAGE_BYTES(DP);
         const float2* xs = reinterpret_cast<const float2*>(stage);
-        const float* ns = reinterpret_cast<const float*>(stage + KTC_TILE * DP * 8);
+        const float* ns = reinterpret_cast<const float*>(stage + KTC_TILE * KTC_LD(DP) * 8);
 #pragma unroll 4
         for (int j8 = 0; j8 < KTC_TILE / 8; ++j8) {
             const float2 nn = *reinterpret_cast<const float2*>(ns + j8 * 8 + 2 * t);
             float c[4] = {nn.x, nn.y, nn.x, nn.y};
 #pragma unroll
             for (int ks = 0; ks < KS; ++ks) {
-                const float2 b0 = xs[(j8 * 8 + g) * DP + ks * 8 + t];
-                const float2 b1 = xs[(j8 * 8 + g) * DP + ks * 8 + t + 4];
+                const float2 b0 = xs[(j8 * 8 + g) * KTC_LD(DP) + ks * 8 + t];
+                const float2 b1 = xs[(j8 * 8 + g) * KTC_LD(DP) + ks * 8 + t + 4];
                 const unsigned bh0 = __float_as_uint(b0.x), bh1 = __float_as_uint(b1.x);
                 const unsigned bl0 = __float_as_uint(b0.y), bl1 = __float_as_uint(b1.y);
                 mma_tf32_16x8x8(c, alo[ks], bh0, bh1);  // small terms first
                 mma_tf32_16x8x8(c, ahi[ks], bl0, bl1);
                 mma_tf32_16x8x8(c, ahi[ks], bh0, bh1);
             }
-            const int j = tl * KTC_TILE + j8 * 8 + 2 * t;
-            if (c[0] < v0[KTC_KP - 1]) ktc_insert(v0, i0, c[0], j);
-            if (c[1] < v0[KTC_KP - 1]) ktc_insert(v0, i0, c[1], j + 1);
-            if (c[2] < v1[KTC_KP - 1]) ktc_insert(v1, i1, c[2], j);
-            if (c[3] < v1[KTC_KP - 1]) ktc_insert(v1, i1, c[3], j + 1);
+            // almost never taken after the first tiles: one warp-uniform branch keeps the (long, predicated) insertion
+            // code out of the steady-state instruction stream
+            const bool hit = fminf(c[0], c[1]) < v0[KTC_KP - 1] || fminf(c[2], c[3]) < v1[KTC_KP - 1];
+            if (__any_sync(0xffffffffu, hit)) {
+                const int j = tl * KTC_TILE + j8 * 8 + 2 * t;
+                if (c[0] < v0[KTC_KP - 1]) ktc_insert(v0, i0, c[0], j);
+                if (c[1] < v0[KTC_KP - 1]) ktc_insert(v0, i0, c[1], j + 1);
+                if (c[2] < v1[KTC_KP - 1]) ktc_insert(v1, i1, c[2], j);
+                if (c[3] < v1[KTC_KP - 1]) ktc_insert(v1, i1, c[3], j + 1);
+            }
         }
         __syncthreads();
     }
@@ -286,7 +296,9 @@ k_knn_tc(const float2* __restrict__ Xp, const float* __restrict__ xn, const floa
             }
     }
     if (!certain || bi[k - 1] == 0x7fffffff) {
-        out[q] = -1;  // handed to the exact brute-force kernel
+        out[q] = -1;  // handed to the exact brute-force kernel: listed for its dense pass (the mark alone if the list is full)
+        const int pos = atomicAdd(qcount, 1);
+        if (pos < qcap) qlist[pos] = q;
         return;
     }
     // uniform vote, smallest label on ties (same rule as knn.cuh)

@@ -323,3 +323,18 @@ k_rowdot(const double* __restrict__ A, const double* __restrict__ B, long long r
     s = warp_sum(s);
     if (lane == 0) out[r] = s;
 }
+
+// ---- dense quadratic-form scan (MSPE): value = (c0 - q + penalty) / n_c, the caller MINIMISES it, so the bucket-ordered
+// array for the arg-max holds -value (first maximum = lowest cluster id, then lowest candidate index).
+// grid ceil(rows/256), block 256
+__global__ void __launch_bounds__(256)
+k_quadform_finish(const double* __restrict__ q, long long rows, long long pos0, const long long* __restrict__ perm, double c0,
+                  double n_c, const double* __restrict__ penalty, double* __restrict__ value_out,
+                  double* __restrict__ neg_sorted) {
+    const long long r = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (r >= rows) return;
+    const long long orig = perm[pos0 + r];
+    const double v = ((c0 - q[r]) + (penalty ? penalty[orig] : 0.0)) / n_c;
+    if (value_out) value_out[orig] = v;
+    neg_sorted[pos0 + r] = -v;
+}

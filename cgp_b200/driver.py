@@ -212,15 +212,8 @@ class cGP_constrained(object):
                     mode = "acquisition"
                 fitted_n, fitted_labels = n, labels.copy()
                 Q = self._candidates(bounds)
-                if self.ACQUISITION == "MSPE":  # minimised, REF/cGP/acquisition.py:69-75
-                    pen = self.boundary_penalty(Q, X)
-                    if np.isscalar(pen) and pen == 0:
-                        X_next, score, idx = model.select_next_mspe(Q)
-                    else:
-                        lab_q = model.predict_labels(Q)
-                        sc = model.mspe_candidates(Q) + np.asarray(pen, dtype=np.float64) / np.bincount(labels)[lab_q]
-                        idx = int(np.lexsort((np.arange(sc.shape[0]), lab_q, sc))[0])
-                        X_next, score = Q[idx], float(sc[idx])
+                if self.ACQUISITION == "MSPE":  # minimised, (mspe + boundary_penalty) / n_c, REF/cGP/acquisition.py:69-75
+                    X_next, score, idx = model.select_next_mspe(Q, boundary_penalty=self.boundary_penalty)
                 else:  # soft constraint inside the GPU score: (EI + boundary_penalty(x, X_c)) / n_c (REF/cGP/acquisition.py:29-32)
                     X_next, score, idx = model.select_next(Q, prune=bool(self.PRUNED_SCAN), boundary_penalty=self.boundary_penalty)
                 self.history.append(dict(step=it, mode=mode, score=float(score), n_clusters=int(labels.max()) + 1))

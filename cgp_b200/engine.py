@@ -121,7 +121,9 @@ class ClusterGPEngine:
         have = 0 if self._ws is None else self._ws.numel()
         if have >= nbytes or (partial_ok and self._ws_capped and have > 0):
             return self._ws
-        # cudaMemGetInfo is slow (measured: up to 59 ms per call on a busy B200) -> only when the workspace must grow
+        # cudaMemGetInfo is slow (measured: up to 59 ms per call on a busy B200) -> only when the workspace must grow.
+        # Blocks cached by torch's allocator (e.g. the factors of a previous model) do not count as free: release them.
+        torch.cuda.empty_cache()
         free, _total = torch.cuda.mem_get_info(self.device)
         budget = int((free + have) * self.mem_fraction)
         if partial_ok:
@@ -354,11 +356,12 @@ class ClusterGPEngine:
         for lane in range(1, n_lanes):
             self._lane_stream(lane).wait_stream(cur)  # the training arrays were uploaded on the caller's stream
         multi = [False]
+        small = int(self.counts.max()) < 2048  # small matrices: the host's share of a step is never negligible
 
         def lane_policy(active):
             # many runs: two lanes hide the host's L-BFGS-B work behind the device; few runs: two lanes overlap the
             # latency-bound chain of one batch with the bulk of the other; in between one batch fills the device
-            use = n_lanes if (active > pipe_min or active <= lane_max) else 1
+            use = n_lanes if (active > pipe_min or active <= lane_max or small) else 1
             multi[0] = use > 1
             return use
 
@@ -625,13 +628,20 @@ class ClusterGPEngine:
         return torch.from_numpy(pen).to(self.device)
 
     # ------------------------------------------------------------------ MSPE (the reference's second acquisition)
-    def _mspe_factors(self, c):
-        """Per-cluster matrices of the dense MSPE scan, padded [npad, npad], normalised-target units:
-        GT = I - Ko Kinv and Soo = Ko + noise I - Ko Kinv Ko, with Ko = Matern(X_c, X_c) (no White term: it is the
-        cross kernel K_trans of SK/_gpr.py:447) and Kinv = W^T W.  s_xo = k*^T G and S_oo are the blocks of the joint
-        posterior covariance `predict([x; X_sample], return_cov=True)` that REF/cGP/acquisition.py:52-57 slices."""
-        cache = self.model.setdefault("_mspe", {})
-        if c not in cache:
+    def _mspe_matrix(self):
+        """B_c of the dense MSPE scan for every cluster, packed like W ([npad, npad] blocks), and c0[c] (host).
+        REF/cGP/acquisition.py:52-68 takes the joint posterior covariance of [x; X_c] (predict(return_cov=True),
+        SK/_gpr.py:464-478, every block scaled by y_std^2) and forms  mspe = s_xx - s_xo S_oo s_xo^T.  With
+        Ko = Matern(X_c, X_c) (no White term: the cross kernel), K^-1 = W^T W, G = I - K^-1 Ko, S~ = Ko + s2 I - Ko K^-1 Ko:
+            s_xx = ys^2 (1 + s2 - k*^T K^-1 k*),  s_xo = ys^2 k*^T G,  S_oo = ys^2 S~
+            mspe = c0 - k*^T B k*,   c0 = ys^2 (1 + s2),   B = ys^2 K^-1 + ys^6 G S~ G^T        (symmetric, per cluster)
+        Five [n_c, n_c] DMMA products per cluster, once per fitted model (cached until the model changes)."""
+        cache = self.model.get("_mspe")
+        if cache is not None:
+            return cache
+        B = torch.zeros(int(self.moff[-1]), dtype=torch.float64, device=self.device)
+        c0 = np.zeros(self.C)
+        for c in range(self.C):
             n, npad = int(self.counts[c]), int(self.npad[c])
             th = self.model["theta_dev"][c].contiguous()
             Xt = self.Xs[int(self.offs[c]):int(self.offs[c + 1])]
@@ -640,58 +650,62 @@ class ClusterGPEngine:
             W = self.model["W"][int(self.moff[c]):int(self.moff[c + 1])].view(npad, npad)
             Wt = W.t().contiguous()
             Kinv = _lib.dgemm_nt(Wt, Wt)          # W^T W (pad block: identity)
-            KoKinv = _lib.dgemm_nt(Ko, Kinv)      # Ko Kinv (both symmetric)
-            GT = -KoKinv
-            GT.diagonal().add_(1.0)
+            KoKinv = _lib.dgemm_nt(Ko, Kinv)      # Ko K^-1 (both symmetric)
+            G = (-KoKinv).t().contiguous()        # G = I - K^-1 Ko
+            G.diagonal().add_(1.0)
             Soo = Ko - _lib.dgemm_nt(KoKinv, Ko)
-            Soo.diagonal()[:n].add_(float(np.exp(self.theta[c][self.d])))
-            cache[c] = (GT, Soo)
-        return cache[c]
+            noise = float(np.exp(self.theta[c][self.d]))
+            Soo.diagonal()[:n].add_(noise)
+            H = _lib.dgemm_nt(_lib.dgemm_nt(G, Soo), G)  # G S~ G^T
+            ys = float(self.y_std[c])
+            Bc = B[int(self.moff[c]):int(self.moff[c + 1])].view(npad, npad)
+            Bc[:n, :n] = (ys ** 2) * Kinv[:n, :n] + (ys ** 6) * H[:n, :n]
+            c0[c] = ys * ys * (1.0 + noise)
+        self.model["_mspe"] = (B, c0)
+        return B, c0
 
-    def mspe_scan(self, Q, k=3, idx_base=0, want_arrays=False, qlabel=None, chunk=16384):
+    def mspe_scan(self, Q, k=3, idx_base=0, want_arrays=False, qlabel=None, penalty=None):
         """Dense scan of REF/cGP/acquisition.py:34-75 over candidates Q: for every candidate x routed to cluster c,
-        ``mspe = s_xx - s_xo S_oo s_xo^T`` from the joint posterior covariance of [x; X_c] (in the reference's units:
-        every covariance block carries y_std^2), value ``mspe / n_c``; the reference MINIMISES it, so the selected
-        candidate is the minimum, ties -> lowest cluster id, then lowest candidate index.
-        The two products are [m, n_c] x [n_c, n_c] GEMMs through the DMMA tile GEMM (cgp_dgemm_nt).
+        ``value = (mspe(x) + penalty) / n_c`` with ``mspe = s_xx - s_xo S_oo s_xo^T`` (see _mspe_matrix); the reference
+        MINIMISES it, so the selected candidate is the minimum, ties -> lowest cluster id, then lowest candidate index.
+        One fused pass per candidate chunk in the C library (cgp_quadform_scan: cross kernel, one DMMA product, row dot).
         -> ((value, idx, cluster) 1-element CUDA tensors, value array in candidate order | None)."""
         Qd = self._to_dev(Q)
-        M = Qd.shape[0]
         if qlabel is None:
             qlabel = self.route(Qd, k)
-        perm = torch.argsort(qlabel, stable=True)  # bucket order: cluster-major, candidate-index-minor
-        cnt = torch.bincount(qlabel, minlength=self.C)
-        coff = torch.zeros(self.C + 1, dtype=torch.int64, device=self.device)
-        coff[1:] = torch.cumsum(cnt, 0)
-        hoff = coff.cpu().numpy()
-        neg_sorted = torch.empty(M, dtype=torch.float64, device=self.device)
-        for c in range(self.C):
-            n, npad = int(self.counts[c]), int(self.npad[c])
-            if hoff[c + 1] == hoff[c]:
-                continue
-            GT, Soo = self._mspe_factors(c)
-            th = self.model["theta_dev"][c].contiguous()
-            Xt = self.Xs[int(self.offs[c]):int(self.offs[c + 1])]
-            ys = float(self.y_std[c])
-            for p0 in range(int(hoff[c]), int(hoff[c + 1]), chunk):
-                p1 = min(int(hoff[c + 1]), p0 + chunk)
-                m = p1 - p0
-                Qc = Qd[perm[p0:p1]].contiguous()
-                mpad = _lib.padded_n(m)
-                Ks = torch.zeros((mpad, npad), dtype=torch.float64, device=self.device)
-                Ks[:m, :n] = _lib.kernel_cross(Qc, Xt, th, self.kind)
-                Sxo = _lib.dgemm_nt(Ks, GT)      # s_xo = k*^T (I - Kinv Ko)
-                T2 = _lib.dgemm_nt(Sxo, Soo)     # s_xo S_oo
-                q = _lib.rowdot(T2, Sxo, n)[:m]
-                ql = torch.full((m,), c, dtype=torch.int64, device=self.device)
-                _, sd = self.predict(Qc, qlabel=ql, return_std=True)
-                neg_sorted[p0:p1] = -((sd * sd - (ys ** 6) * q) / float(n))
-        best = _lib.argmax_sorted(neg_sorted, perm, coff, idx_base)
-        arr = None
-        if want_arrays:
-            arr = torch.empty(M, dtype=torch.float64, device=self.device)
-            arr[perm] = -neg_sorted
-        return (-best[0], best[1], best[2]), arr
+        if penalty is not None and not isinstance(penalty, torch.Tensor):
+            penalty = torch.from_numpy(np.ascontiguousarray(np.asarray(penalty, dtype=np.float64).reshape(-1))).to(self.device)
+        B, c0 = self._mspe_matrix()
+        ws = self._workspace(_lib.quadform_workspace_bytes(self.offs, self.d, Qd.shape[0]))
+        return _lib.quadform_scan(self.Xs, self.offs, self.model["theta_dev"], B, c0, Qd, qlabel, self.kind, idx_base,
+                                  penalty, want_arrays, ws)
+
+    def select_next_mspe(self, candidates, k=3, sharded=False, boundary_penalty=None):
+        """MSPE counterpart of select_next: candidates sharded over ranks, each rank scans its shard, all-gather of the
+        per-rank minima with the reference's tie rule, broadcast of the selected point.
+        -> (x_next np[d], value, global idx, cluster)."""
+        rank, ws = cdist.world()
+        local, base = self._local_shard(candidates, sharded, rank, ws)
+        ql = self.route(local, k)
+        pen = None if boundary_penalty is None else self.penalty_of(local, ql, boundary_penalty)
+        (bv, bi, bc), _ = self.mspe_scan(local, k, idx_base=base, qlabel=ql, penalty=pen)
+        li = int(bi.item()) - base
+        x_local = local[li] if li >= 0 else torch.zeros(self.d, dtype=torch.float64, device=self.device)
+        neg, idx, cl, x, _owner = cdist.reduce_best(-bv, bi, bc, x_local, rank, ws)
+        return x.cpu().numpy(), -neg, idx, cl
+
+    def _local_shard(self, candidates, sharded, rank, ws):
+        """This rank's candidates and the global index of its first one (see select_next)."""
+        if sharded:
+            local = self._to_dev(candidates)
+            sizes = torch.tensor([local.shape[0]], dtype=torch.int64, device=self.device)
+            if ws > 1:
+                alls = torch.empty(ws, dtype=torch.int64, device=self.device)
+                torch.distributed.all_gather_into_tensor(alls, sizes)
+                return local, int(alls[:rank].sum().item())
+            return local, 0
+        lo, hi = cdist.shard_range(candidates.shape[0], rank, ws)
+        return self._to_dev(candidates[lo:hi]), lo
 
     def select_next(self, candidates, k=3, sharded=False, prune=True, boundary_penalty=None):
         """Pick the next sample from `candidates` [M,d].
@@ -704,20 +718,7 @@ class ClusterGPEngine:
         boundary_penalty: the reference's soft-constraint hook (X, data_X) -> additive term (see penalty_of); it is added
         to EI inside the GPU score, (EI + penalty) / n_c."""
         rank, ws = cdist.world()
-        if sharded:
-            local = self._to_dev(candidates)
-            sizes = torch.tensor([local.shape[0]], dtype=torch.int64, device=self.device)
-            if ws > 1:
-                alls = torch.empty(ws, dtype=torch.int64, device=self.device)
-                torch.distributed.all_gather_into_tensor(alls, sizes)
-                base = int(alls[:rank].sum().item())
-            else:
-                base = 0
-        else:
-            M = candidates.shape[0]
-            lo, hi = cdist.shard_range(M, rank, ws)
-            local = self._to_dev(candidates[lo:hi])
-            base = lo
+        local, base = self._local_shard(candidates, sharded, rank, ws)
         ql = self.route(local, k)
         pen = None if boundary_penalty is None else self.penalty_of(local, ql, boundary_penalty)
         (bs, bi, bc), _ = self.ei_scan(local, k, idx_base=base, prune=prune, qlabel=ql, penalty=pen)

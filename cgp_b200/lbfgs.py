@@ -199,6 +199,7 @@ class StealBoard:
         self._load = 0
         self._served = 0
         self._pending = None  # (victim, k) of the one request in flight
+        self._last_poll = 0.0
         self.stolen = 0
         self.given = 0
 
@@ -217,10 +218,17 @@ class StealBoard:
     def all_done(self):
         return self.store.add(self._k("done"), 0) >= self.total
 
-    def maybe_request(self, my_load):
-        """Post a request to the busiest rank if it holds at least two runs more than this rank."""
+    def maybe_request(self, my_load, min_interval=2e-3):
+        """Post a request to the busiest rank if it holds at least two runs more than this rank.  The loads of the other
+        ranks are read at most every `min_interval` seconds (one store round trip per rank)."""
         if self._pending is not None:
             return
+        import time
+
+        now = time.perf_counter()
+        if now - self._last_poll < min_interval:
+            return
+        self._last_poll = now
         loads = [self.store.add(self._k(f"load/{r}"), 0) if r != self.rank else -1 for r in range(self.world)]
         v = int(np.argmax(loads))
         if loads[v] < my_load + 2:

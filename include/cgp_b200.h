@@ -165,6 +165,20 @@ int cgp_refresh_alpha(cgp_handle* h, const double* L, const double* W, int64_t n
                       const double* y, double* alpha_out, double* lml, void* workspace,
                       size_t workspace_bytes, void* stream);
 
+/* Dense MSPE scan, the reference's second acquisition (REF/cGP/acquisition.py:34-75, minimised :75) over m candidates:
+ *   mspe(x) = s_xx - s_xo S_oo s_xo^T  from the joint posterior covariance of [x; X_c]  =  c0[c] - k*^T B_c k*
+ * with the per-cluster symmetric matrix B_c = ys^2 K^-1 + ys^6 G S~ G^T (G = I - K^-1 K_o, S~ = K_o + s2 I - K_o K^-1 K_o;
+ * built once per cluster by the caller with cgp_dgemm_nt) and c0[c] = ys^2 (1 + s2); value_i = (mspe_i + penalty_i) / n_c.
+ * One [rows, n_c] x [n_c, n_c] DMMA product + a row dot per candidate chunk.  best_value holds MINUS the minimum
+ * (the arg-max machinery of cgp_ei_argmax runs on -value); ties -> lowest cluster id, then lowest candidate index.
+ *   Bmat  per-cluster [npad, npad] blocks, packed like W;  c0 [n_clusters] HOST array;  value [m] optional. */
+size_t cgp_quadform_workspace_bytes(const int64_t* offs_host, int n_clusters, int d, int64_t m);
+int cgp_quadform_scan(cgp_handle* h, int kind, const double* X, const int64_t* offs_host, int n_clusters, int d,
+                      const double* theta, const double* Bmat, const double* c0_host, const double* Q,
+                      const int64_t* qlabel, int64_t m, int64_t idx_base, const double* penalty, double* value,
+                      double* best_value, int64_t* best_idx, int64_t* best_cluster, void* workspace,
+                      size_t workspace_bytes, void* stream);
+
 /* Building blocks of the dense MSPE scan (the reference's second acquisition, REF/cGP/acquisition.py:34-75: joint
  * posterior covariance of [x; X_sample] from predict(return_cov=True), mspe = s_xx - s_xo S_oo s_xo^T).  As a scan over
  * m candidates the two products are [m, n_c] x [n_c, n_c] GEMMs through cgp_dgemm_nt (cgp_b200/engine.py mspe_scan);

@@ -30,7 +30,8 @@ def _run(mode, R=5):
     x, score, idx, cl = eng.select_next(Q, k=3)
     xe, se, ie, ce = eng.select_next(Q, k=3, prune=False)
     assert (idx, cl) == (ie, ce) and score == se
-    return dict(theta=eng.theta.copy(), lml=eng.model["lml_host"].copy(), x=x, score=score, idx=idx, cluster=cl,
+    xm, vm, im, cm = eng.select_next_mspe(Q, k=3)  # the second acquisition, candidates sharded the same way
+    return dict(mspe=(vm, im, cm, xm.tolist()), theta=eng.theta.copy(), lml=eng.model["lml_host"].copy(), x=x, score=score, idx=idx, cluster=cl,
                 evals=eng.fit_stats["evals"], nfev=eng.fit_stats["nfev"].copy(), stats={k: v for k, v in eng.fit_stats.items()
                                                                                        if k in ("stolen", "given", "lanes")})
 
@@ -76,6 +77,7 @@ def test_two_ranks_select_the_same_sample_as_one():
             assert np.array_equal(got["lml"], ref["lml"]) and np.array_equal(got["nfev"], ref["nfev"])
             assert got["idx"] == ref["idx"] and got["cluster"] == ref["cluster"] and got["score"] == ref["score"]
             assert np.array_equal(got["x"], ref["x"])
+            assert got["mspe"] == ref["mspe"], (rank, mode, got["mspe"], ref["mspe"])
     # the work was really shared: no rank evaluated everything, together they evaluated exactly the single-rank count
     for mode in ("async", "balanced", "static"):
         e0, e1 = res[0][mode]["evals"], res[1][mode]["evals"]

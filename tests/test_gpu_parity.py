@@ -368,7 +368,7 @@ def test_return_cov_and_mspe_vs_reference():
 
 
 def test_dense_mspe_scan_vs_reference_pointwise():
-    """The dense MSPE scan (engine.mspe_scan: two [m, n_c] x [n_c, n_c] DMMA GEMMs + row dot) against (a) the
+    """The dense MSPE scan (engine.mspe_scan -> cgp_quadform_scan: one [m, n_c] x [n_c, n_c] DMMA product + row dot) against (a) the
     reference's own outputs for a single cluster (tests/golden/cov_mspe_d3.npz, made by REF/cGP/acquisition.py:34-75)
     and (b) the point-wise restatement with scikit-learn surrogates on a two-cluster model; selection = minimum,
     ties to the lowest cluster id then index."""
@@ -414,6 +414,15 @@ def test_dense_mspe_scan_vs_reference_pointwise():
             assert abs(arr[q] - want) <= 1e-6 * max(abs(want), 1e-12), (cc, q, arr[q], want)
     order = np.lexsort((np.arange(M), ql, arr))  # minimum; ties -> lowest cluster id, then lowest index
     assert int(i.item()) == int(order[0]) and int(c.item()) == int(ql[order[0]]) and float(v.item()) == arr[order[0]]
+    # additive soft-constraint term inside the scan: (mspe + penalty) / n_c, REF/cGP/acquisition.py:69,75
+    pen = rng.uniform(0, 1e-3, size=M)
+    (vp, ip, cp), arrp = eng.mspe_scan(Qs, 3, want_arrays=True, penalty=pen)
+    n_c = np.bincount(lab)[ql]
+    assert np.max(np.abs(arrp.cpu().numpy() - (arr + pen / n_c))) <= 1e-15 * np.max(np.abs(arr + pen / n_c)) + 1e-18
+    op = np.lexsort((np.arange(M), ql, arrp.cpu().numpy()))
+    assert int(ip.item()) == int(op[0])
+    x, val, idx, cl = eng.select_next_mspe(Qs, 3)
+    assert idx == int(order[0]) and val == arr[order[0]] and np.array_equal(x, Qs[idx])
 
 
 def test_workspace_hygiene_nan_fill_and_canaries(lib):
