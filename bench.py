@@ -427,12 +427,11 @@ def run_b200(args, preset):
     prof = _lib.profile_read(reset=True, device=local, detail=True)
     _lib.profile_enable(False, local)
     step_s = t_dev / args.steps
-    res = dict(stats)
+    res = {k: v for k, v in stats.items() if k != "_model"}  # no second reference to the model (configs[3]: 69 GB)
     t_e2e, _ = timed(args.steps, Q_pin, True)
     e2e_s = t_e2e / args.steps
     # outside every timed region: the EXHAUSTIVE scan on the same fitted model (every candidate scored)
     model = stats.pop("_model")
-    res.pop("_model", None)
     exhaustive = None
     if not args.no_exhaustive and preset != "cfg4":  # cfg4: 8M x 65536^2 flops = 18 min on one GPU
         barrier()

@@ -41,7 +41,7 @@ SIGNATURES = {
                               _vp, _vp, _vp, _sz, _vp]),
     "cgp_ei_argmax": (C.c_int, [_vp, C.c_int, _vp, _pi64, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                 _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
-    "cgp_ei_argmax_pruned": (C.c_int, [_vp, C.c_int, _vp, _pi64, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+    "cgp_ei_argmax_pruned": (C.c_int, [_vp, C.c_int, _vp, _pi64, C.c_int, C.c_int, _vp, _f64, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                        _i64, _i64, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "cgp_append_workspace_bytes": (_sz, [_i64]),
     "cgp_append_sample": (C.c_int, [_vp, C.c_int, _vp, _i64, C.c_int, _vp, _f64, _vp, _vp, _i64, _vp, _vp, _sz, _vp]),
@@ -336,7 +336,7 @@ def predict(X, offs, theta, W, alpha_vec, y_mean, y_std, Q, qlabel, kind, want_s
 
 
 def ei_argmax(X, offs, theta, W, alpha_vec, y_mean, y_std, y_max, Q, qlabel, kind, idx_base=0, want_arrays=False,
-              workspace=None, prune=False, penalty=None):
+              workspace=None, prune=False, penalty=None, alpha=None):
     """-> (best [score f64, idx i64, cluster i64] as CUDA tensors, score/mean/std arrays or None).
     prune=True: exact bound-pruned scan (cgp_ei_argmax_pruned): same selection, no per-candidate arrays.
     penalty: [m] CUDA f64 additive soft-constraint term (score = (EI + penalty) / n_c) or None."""
@@ -359,7 +359,9 @@ def ei_argmax(X, offs, theta, W, alpha_vec, y_mean, y_std, y_max, Q, qlabel, kin
     if prune:
         if want_arrays:
             raise CgpError("the pruned scan has no per-candidate outputs (pruned candidates are never scored exactly)")
-        _chk(lib().cgp_ei_argmax_pruned(handle(dev.index), KIND[kind], _ptr(X), po, len(o) - 1, d, _ptr(theta), _ptr(W),
+        if alpha is None:
+            raise CgpError("the pruned scan needs the jitter `alpha` the model was factorised with (single-neighbour bound)")
+        _chk(lib().cgp_ei_argmax_pruned(handle(dev.index), KIND[kind], _ptr(X), po, len(o) - 1, d, _ptr(theta), float(alpha), _ptr(W),
                                         _ptr(alpha_vec), _ptr(y_mean), _ptr(y_std), _ptr(y_max), _ptr(Q),
                                         _ptr(qlabel, torch.int64), m, int(idx_base), _ptr(penalty), _ptr(bs),
                                         _ptr(bi, torch.int64), _ptr(bc, torch.int64), _ptr(workspace, torch.uint8),

@@ -957,7 +957,7 @@ struct ScoreLayout {
     int64_t mch;  // candidates per chunk (multiple of 128)
     int nblk, Tmax;
     int64_t npad_max;
-    size_t o_perm, o_qs, o_sorted, o_hist, o_blkoff, o_coff, o_blkv, o_blkp, o_kstar, o_vpart, o_mraw, o_sel, o_cnt, o_lb, total;
+    size_t o_perm, o_qs, o_sorted, o_hist, o_blkoff, o_coff, o_blkv, o_blkp, o_kstar, o_vpart, o_mraw, o_kmax, o_sel, o_cnt, o_lb, total;
 };
 
 static ScoreLayout score_layout(const int64_t* offs, int C, int d, int64_t m) {
@@ -989,6 +989,7 @@ static ScoreLayout score_layout(const int64_t* offs, int C, int d, int64_t m) {
     L.o_kstar = take((size_t)mch * L.npad_max * 8);
     L.o_vpart = take((size_t)L.Tmax * mch * 8);
     L.o_mraw = take((size_t)mch * 8);
+    L.o_kmax = take((size_t)mch * 8);
     L.o_sel = take((size_t)mch * 4);
     L.o_cnt = take(8);
     L.o_lb = take(8);
@@ -1006,7 +1007,7 @@ static int run_score(HandleImpl* h, int kind, const double* X, const int64_t* of
                      const double* y_max, const double* Q, const int64_t* qlabel, int64_t m, int64_t idx_base,
                      double* score, double* mean, double* std_, double* best_score, int64_t* best_idx,
                      int64_t* best_cluster, void* workspace, size_t ws_bytes, cudaStream_t s, bool prune = false,
-                     const double* penalty = nullptr) {
+                     const double* penalty = nullptr, double alpha = 0.0) {
     if (C > 4096) return -5;
     ScoreLayout L = score_layout(offs, C, d, m);
     if (L.total > ws_bytes) return -100;
@@ -1022,6 +1023,7 @@ static int run_score(HandleImpl* h, int kind, const double* X, const int64_t* of
     double* kstar = reinterpret_cast<double*>(ws + L.o_kstar);
     double* vpart = reinterpret_cast<double*>(ws + L.o_vpart);
     double* mraw = reinterpret_cast<double*>(ws + L.o_mraw);
+    double* kmaxv = reinterpret_cast<double*>(ws + L.o_kmax);
     int* sel = reinterpret_cast<int*>(ws + L.o_sel);
     int* cnt = reinterpret_cast<int*>(ws + L.o_cnt);
     double* lb = reinterpret_cast<double*>(ws + L.o_lb);
@@ -1051,10 +1053,12 @@ static int run_score(HandleImpl* h, int kind, const double* X, const int64_t* of
             const long long rows_pad = pad_n(rows);
             int rc = launch_cross(h, kind, Qs + p0 * d, rows, Xc, n, d, th, kstar, npad, rows_pad, npad, 0, 0.0, s);
             if (rc) return rc;
-            KL(h, CLS_MEAN, s, k_mean<<<(unsigned)((rows + 7) / 8), 256, 0, s>>>(kstar, alpha_vec + offs[c], (int)n, (int)npad, rows, mraw));
+            KL(h, CLS_MEAN, s, k_mean<<<(unsigned)((rows + 7) / 8), 256, 0, s>>>(kstar, alpha_vec + offs[c], (int)n, (int)npad, rows, mraw,
+                                                                              prune ? kmaxv : nullptr));
             if (prune) {  // mean-only bound -> survivors -> exact variance / score of the survivors -> tighter bound
                 KL(h, CLS_SCORE_FINISH, s, k_prune_select<<<1, 1024, 0, s>>>(mraw, rows, th, d, y_mean, y_std, y_max, c, (double)n, lb,
-                                                                              sel, cnt, sorted + p0, penalty, perm + p0));
+                                                                              sel, cnt, sorted + p0, penalty, perm + p0, kmaxv,
+                                                                              alpha));
                 KL(h, CLS_PREDICT_VNORM, s, k_predict_vnorm_sel<<<(unsigned)((rows_pad / CGP_TILE) * T), CGP_GEMM_THREADS, GEMM_SMEM_BYTES, s>>>(
                     Wc, kstar, vpart, (int)npad, L.mch, sel, cnt));
                 KL(h, CLS_SCORE_FINISH, s, k_score_finish_sel<<<(unsigned)((rows + 255) / 256), 256, 0, s>>>(
@@ -1135,7 +1139,7 @@ extern "C" int cgp_ei_argmax(cgp_handle* hh, int kind, const double* X, const in
 }
 
 extern "C" int cgp_ei_argmax_pruned(cgp_handle* hh, int kind, const double* X, const int64_t* offs, int C, int d,
-                                    const double* theta, const double* W, const double* alpha_vec, const double* y_mean,
+                                    const double* theta, double alpha, const double* W, const double* alpha_vec, const double* y_mean,
                                     const double* y_std, const double* y_max, const double* Q, const int64_t* qlabel,
                                     int64_t m, int64_t idx_base, const double* penalty, double* best_score, int64_t* best_idx,
                                     int64_t* best_cluster, void* workspace, size_t ws_bytes, void* stream) {
@@ -1145,21 +1149,22 @@ extern "C" int cgp_ei_argmax_pruned(cgp_handle* hh, int kind, const double* X, c
     if (!offs || C <= 0) return -4;
     if (d < 1 || d > CGP_MAX_D) return -6;
     if (!theta) return -7;
-    if (!W) return -8;
-    if (!alpha_vec) return -9;
-    if (!y_mean) return -10;
-    if (!y_std) return -11;
-    if (!y_max) return -12;
-    if (m <= 0) return -15;
-    if (!Q) return -13;
-    if (!qlabel) return -14;
+    if (!(alpha >= 0.0)) return -8;
+    if (!W) return -9;
+    if (!alpha_vec) return -10;
+    if (!y_mean) return -11;
+    if (!y_std) return -12;
+    if (!y_max) return -13;
+    if (m <= 0) return -16;
+    if (!Q) return -14;
+    if (!qlabel) return -15;
     if (!best_score) return -17;
     if (!best_idx) return -18;
     if (!best_cluster) return -19;
     if (!workspace) return -20;
     return run_score(h, kind, X, offs, C, d, theta, W, alpha_vec, y_mean, y_std, y_max, Q, qlabel, m, idx_base, nullptr,
                      nullptr, nullptr, best_score, best_idx, best_cluster, workspace, ws_bytes, (cudaStream_t)stream, true,
-                     penalty);
+                     penalty, alpha);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -88,17 +88,30 @@ k_bucket_scatter(const long long* __restrict__ qlabel, const double* __restrict_
 }
 
 // ---- predictive mean: mraw[r] = sum_{k<n} Kstar[r,k] alpha[k].  warp per row; grid (ceil(rows/8)), block 256
+// kmax (optional): kmax[r] = max_k |Kstar[r,k]|, the cross-kernel value of the nearest training point (input of the
+// single-neighbour variance bound of the pruned scan).
 __global__ void __launch_bounds__(256)
 k_mean(const double* __restrict__ Kstar, const double* __restrict__ alpha, int n, int npad, long long rows,
-       double* __restrict__ mraw) {
+       double* __restrict__ mraw, double* __restrict__ kmax) {
     const long long r = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (r >= rows) return;
     const double* kr = Kstar + r * npad;
-    double s = 0.0;
-    for (int k = lane; k < n; k += 32) s += kr[k] * alpha[k];
+    double s = 0.0, mx = 0.0;
+    for (int k = lane; k < n; k += 32) {
+        const double v = kr[k];
+        s += v * alpha[k];
+        mx = fmax(mx, fabs(v));
+    }
     s = warp_sum(s);
-    if (lane == 0) mraw[r] = s;
+    if (kmax) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    if (lane == 0) {
+        mraw[r] = s;
+        if (kmax) kmax[r] = mx;
+    }
 }
 
 __device__ __forceinline__ double ei_value(double mean, double sd, double ymax) {
@@ -142,9 +155,14 @@ k_score_finish(const double* __restrict__ vpart, long long vstride, int T, const
 }
 
 // ---- exact bound-pruned scan --------------------------------------------------------------------------------
-// EI(mu, sigma) grows with sigma, and the posterior variance never exceeds the prior variance (1 + noise) y_std^2
-// (it is the prior minus a sum of squares, SK/_gpr.py:482-483).  So  ub = EI(mu, sigma_prior) / n_c  bounds the score
-// of a candidate from its predictive MEAN alone (n_c flops instead of n_c^2).  A candidate whose bound is below the
+// EI(mu, sigma) grows with sigma, and the posterior variance given ALL samples of the cluster never exceeds the
+// posterior variance given only ONE of them (conditioning on more data cannot increase a Gaussian's variance):
+//     var(x) <= (1 + noise) - k(x, x_j)^2 / (1 + noise + alpha)      for every training point j,
+// tightest for the nearest one (largest cross-kernel value kmax, a by-product of the mean pass).  So
+//     ub = EI(mu, sigma_ub) / n_c,  sigma_ub^2 = ((1 + noise) - kmax^2 / (1 + noise + alpha)) y_std^2  (inflated by 1e-6
+// relative + 1e-12 of the prior against rounding of the exact variance) bounds the score of a candidate from its
+// predictive MEAN pass alone (n_c flops instead of n_c^2).  Far from every sample kmax -> 0 and the bound is the prior
+// variance; next to a sample it drops to ~noise.  A candidate whose bound is below the
 // best exact score found so far (`lb`, device scalar) can neither win nor tie; it skips the variance contraction.
 // Survivors are scored exactly as in the exhaustive scan (same bits), so the selected sample is identical.
 // The bound is inflated by 1e-9 relative: the computed EI is monotone in sigma only up to rounding (the two terms of
@@ -154,17 +172,20 @@ __global__ void __launch_bounds__(1024)
 k_prune_select(const double* __restrict__ mraw, long long rows, const double* __restrict__ th, int d,
                const double* __restrict__ ymean, const double* __restrict__ ystd, const double* __restrict__ ymax,
                int cluster, double n_c, const double* __restrict__ lb, int* __restrict__ sel, int* __restrict__ count,
-               double* __restrict__ score_chunk, const double* __restrict__ penalty, const long long* __restrict__ perm_chunk) {
+               double* __restrict__ score_chunk, const double* __restrict__ penalty, const long long* __restrict__ perm_chunk,
+               const double* __restrict__ kmax, double alpha) {
     __shared__ int part[1024];
     const int per = (int)((rows + 1023) / 1024);
     const long long s = (long long)threadIdx.x * per, e = min(rows, s + per);
     const double ys = ystd[cluster], ym = ymean[cluster], yx = ymax[cluster];
-    const double sd_prior = sqrt((1.0 + exp(th[d])) * (ys * ys));
+    const double prior = 1.0 + exp(th[d]), kjj = prior + alpha;
     const double bound = *lb;
     unsigned long long keep = 0ull;  // per <= 64 (chunks hold at most 65536 candidates)
     int c = 0;
     for (long long r = s; r < e; ++r) {
-        double ub = ei_value(ys * mraw[r] + ym, sd_prior, yx);
+        const double km = kmax[r];
+        const double var_ub = fmin(prior, (prior - km * km / kjj) * (1.0 + 1e-6) + 1e-12 * prior);
+        double ub = ei_value(ys * mraw[r] + ym, sqrt(fmax(var_ub, 0.0) * (ys * ys)), yx);
         // the additive penalty shifts bound and score alike; the 1e-9 inflation is applied to the EI part only
         const double pen = penalty ? penalty[perm_chunk[r]] : 0.0;
         ub = (ub * (1.0 + 1e-9) + 1e-300 + pen) / n_c;

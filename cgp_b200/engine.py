@@ -132,6 +132,9 @@ class ClusterGPEngine:
             reserve = 16 * _lib.model_elems(self.offs)
             one_pair = max(_lib.lml_workspace_bytes(self.offs, np.asarray([c], dtype=np.int32), self.d) for c in range(self.C))
             budget = max(budget - reserve, min(one_pair, budget))
+            if budget < min(one_pair, nbytes):
+                raise _lib.CgpError(f"out of device memory: one LML evaluation needs a {one_pair / 2**30:.2f} GiB workspace, "
+                                    f"{budget / 2**30:.2f} GiB are available (mem_fraction={self.mem_fraction})")
         want = min(nbytes, budget)
         if want < nbytes and not partial_ok:
             raise _lib.CgpError(f"out of device memory: this call needs a {nbytes / 2**30:.2f} GiB workspace, the budget is "
@@ -588,7 +591,7 @@ class ClusterGPEngine:
         ws = self._workspace(_lib.score_workspace_bytes(self.offs, self.d, Qd.shape[0]))
         return _lib.ei_argmax(self.Xs, self.offs, m["theta_dev"], m["W"], m["alpha_vec"], self.y_mean_dev,
                               self.y_std_dev, self.y_max_dev, Qd, qlabel, self.kind, idx_base, want_arrays, ws, prune,
-                              penalty=penalty)
+                              penalty=penalty, alpha=self.alpha)
 
     def penalty_of(self, Q, qlabel, boundary_penalty):
         """Evaluate the reference's soft-constraint hook ``boundary_penalty(X, data_X)`` (REF/cGP/acquisition.py:29:

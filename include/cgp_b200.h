@@ -134,11 +134,13 @@ int cgp_ei_argmax(cgp_handle* h, int kind, const double* X, const int64_t* offs_
                   size_t workspace_bytes, void* stream);
 
 /* Same selection as cgp_ei_argmax (identical best_score bits, best_idx, best_cluster) with exact bound pruning:
- * EI grows with sigma and the posterior variance never exceeds the prior one, so EI(mean_i, sigma_prior)/n_c bounds
- * score_i from the predictive mean alone; candidates whose bound is below the best exact score found so far skip the
- * n_c^2 variance contraction.  No per-candidate outputs (pruned candidates have no exact score). */
+ * EI grows with sigma and the posterior variance given all samples never exceeds the one given a single sample,
+ *   var_i <= (1 + s2) - kmax_i^2 / (1 + s2 + alpha),  kmax_i = largest cross-kernel value of candidate i,
+ * so EI(mean_i, sigma_ub_i)/n_c bounds score_i from the predictive-mean pass alone; candidates whose bound is below the
+ * best exact score found so far skip the n_c^2 variance contraction.  alpha = the jitter the model was factorised with
+ * (cgp_factorize).  No per-candidate outputs (pruned candidates have no exact score). */
 int cgp_ei_argmax_pruned(cgp_handle* h, int kind, const double* X, const int64_t* offs_host,
-                         int n_clusters, int d, const double* theta, const double* W,
+                         int n_clusters, int d, const double* theta, double alpha, const double* W,
                          const double* alpha_vec, const double* y_mean, const double* y_std,
                          const double* y_max, const double* Q, const int64_t* qlabel, int64_t m,
                          int64_t idx_base, const double* penalty, double* best_score, int64_t* best_idx,

@@ -485,7 +485,7 @@ def test_workspace_hygiene_nan_fill_and_canaries(lib):
     # pruned scan with a poisoned workspace: same winner, canary intact
     wsp = poisoned(need_s)
     (bs3, bi3, bc3), _ = lib.ei_argmax(Xd, offs, dev(th[:C]), m["W"], m["alpha_vec"], dev(np.zeros(C)), ones, dev(np.zeros(C)),
-                                        dev(Q), ql, "matern32", 0, False, wsp[:need_s], True)
+                                        dev(Q), ql, "matern32", 0, False, wsp[:need_s], True, alpha=1e-5)
     assert canary_ok(wsp, need_s)
     assert int(bi3.item()) == int(bi.item()) and float(bs3.item()) == float(bs.item()) and int(bc3.item()) == int(bc.item())
     # rank-1 append + alpha refresh on poisoned workspaces / poisoned new rows

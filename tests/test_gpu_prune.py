@@ -74,3 +74,49 @@ def test_pruned_scan_rejects_per_candidate_outputs():
     Q = torch.from_numpy(rng.uniform(size=(1000, 2))).cuda()
     with pytest.raises(_lib.CgpError):
         eng.ei_scan(Q, 3, want_arrays=True, prune=True)
+
+
+def test_pruned_scan_candidates_on_top_of_samples():
+    """The single-neighbour variance bound is tightest exactly where the exact variance cancels (candidates on or within
+    1e-9..1e-3 of a training point, noise at its lower bound 1e-5): the bound must still dominate the exact score, i.e.
+    the selection (and its score bits) must equal the exhaustive scan's."""
+    import torch
+
+    from cgp_b200.engine import ClusterGPEngine
+
+    rng = np.random.default_rng(11)
+    n, d, C = 900, 3, 3
+    X = rng.uniform(size=(n, d))
+    lab = np.minimum((X[:, 0] * C).astype(np.int64), C - 1)
+    y = np.sin(7 * X.sum(1)) + lab + 1e-3 * rng.standard_normal(n)
+    for noise in (np.log(1e-5), -6.0, -2.0):
+        eng = ClusterGPEngine(X, y, lab, "matern32", 1e-5).set_theta(np.tile(np.array([-1.0, -0.8, -1.2, noise]), (C, 1)))
+        parts = [X, X + 1e-9 * rng.standard_normal(X.shape), X + 1e-5 * rng.standard_normal(X.shape),
+                 X + 1e-3 * rng.standard_normal(X.shape), rng.uniform(size=(20000, d))]
+        Q = torch.from_numpy(np.clip(np.concatenate(parts), 0, 1)).cuda()
+        _same(eng, Q)
+
+
+def test_pruned_scan_flat_targets_and_incumbents_everywhere():
+    """(a) constant targets in one cluster (y_std falls back to 1, EI of every candidate there is pure sigma * pdf(0));
+    (b) every cluster's incumbent (its best sample) is itself a candidate; (c) the whole candidate set duplicated so that
+    both halves (= the shards of a 2-rank run) hold the same maximum: the lowest index must win in both scans."""
+    import torch
+
+    from cgp_b200.engine import ClusterGPEngine
+
+    rng = np.random.default_rng(12)
+    n, d = 700, 2
+    X = rng.uniform(size=(n, d))
+    lab = (X[:, 1] > 0.5).astype(np.int64)
+    y = np.where(lab == 0, 3.0, np.cos(6 * X[:, 0]) + 0.01 * rng.standard_normal(n))  # cluster 0: exactly flat
+    eng = ClusterGPEngine(X, y, lab, "matern32", 1e-5).set_theta(np.array([[-1.0, -1.0, -5.0], [-1.2, -0.7, -6.0]]))
+    inc = np.stack([X[lab == c][np.argmax(y[lab == c])] for c in range(2)])
+    q = np.concatenate([rng.uniform(size=(15000, d)), inc])
+    Q = torch.from_numpy(np.concatenate([q, q])).cuda()
+    score, idx = _same(eng, Q)
+    assert idx < q.shape[0]  # the first copy wins the exact tie
+    # shard-wise: each half alone picks the same local candidate with the same score bits
+    (s0, i0, _), _ = eng.ei_scan(Q[: q.shape[0]], 3, prune=True)
+    (s1, i1, _), _ = eng.ei_scan(Q[q.shape[0]:], 3, prune=True, idx_base=q.shape[0])
+    assert int(i0.item()) == idx and int(i1.item()) == idx + q.shape[0] and float(s0.item()) == float(s1.item()) == score

@@ -2,11 +2,11 @@
 mkdir -p gpurun_out
 runN() { n=$1; shift; python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus $n "$@"; }
 runN 8 --steps 3 --warmup 2 > gpurun_out/r02e_bench_cfg3_n8_async.json 2> gpurun_out/r02e_bench_cfg3_n8_async.err; echo "n8 async rc=$?"; tail -2 gpurun_out/r02e_bench_cfg3_n8_async.err
-CGP_SHARD_MODE=balanced runN 8 --steps 3 --warmup 2 --no-exhaustive > gpurun_out/r02e_bench_cfg3_n8_balanced.json 2> gpurun_out/r02e_bench_cfg3_n8_balanced.err; echo "n8 bal rc=$?"
-CGP_LANES=3 runN 8 --steps 3 --warmup 2 --no-exhaustive > gpurun_out/r02e_bench_cfg3_n8_lanes3.json 2> gpurun_out/r02e_bench_cfg3_n8_lanes3.err; echo "n8 lanes3 rc=$?"
-CGP_LANES=1 runN 8 --steps 3 --warmup 2 --no-exhaustive > gpurun_out/r02e_bench_cfg3_n8_lanes1.json 2> gpurun_out/r02e_bench_cfg3_n8_lanes1.err; echo "n8 lanes1 rc=$?"
-runN 4 --steps 2 --warmup 2 --no-exhaustive > gpurun_out/r02e_bench_cfg3_n4_async.json 2> gpurun_out/r02e_bench_cfg3_n4_async.err; echo "n4 rc=$?"
-runN 8 --preset cfg5 --steps 2 --warmup 2 > gpurun_out/r02e_bench_cfg5_n8.json 2> gpurun_out/r02e_bench_cfg5_n8.err; echo "cfg5 n8 rc=$?"
+CGP_SHARD_MODE=balanced runN 8 --steps 2 --warmup 1 --no-exhaustive > gpurun_out/r02e_bench_cfg3_n8_balanced.json 2> gpurun_out/r02e_bench_cfg3_n8_balanced.err; echo "n8 bal rc=$?"
+CGP_LANES=3 runN 8 --steps 2 --warmup 1 --no-exhaustive > gpurun_out/r02e_bench_cfg3_n8_lanes3.json 2> gpurun_out/r02e_bench_cfg3_n8_lanes3.err; echo "n8 lanes3 rc=$?"
+CGP_LANES=1 runN 8 --steps 2 --warmup 1 --no-exhaustive > gpurun_out/r02e_bench_cfg3_n8_lanes1.json 2> gpurun_out/r02e_bench_cfg3_n8_lanes1.err; echo "n8 lanes1 rc=$?"
+runN 4 --steps 2 --warmup 1 --no-exhaustive > gpurun_out/r02e_bench_cfg3_n4_async.json 2> gpurun_out/r02e_bench_cfg3_n4_async.err; echo "n4 rc=$?"
+runN 8 --preset cfg5 --steps 2 --warmup 1 > gpurun_out/r02e_bench_cfg5_n8.json 2> gpurun_out/r02e_bench_cfg5_n8.err; echo "cfg5 n8 rc=$?"
 runN 8 --preset cfg4 --steps 1 --warmup 1 > gpurun_out/r02e_bench_cfg4_n8.json 2> gpurun_out/r02e_bench_cfg4_n8.err; echo "cfg4 n8 rc=$?"; tail -3 gpurun_out/r02e_bench_cfg4_n8.err
 for f in gpurun_out/r02e_bench_*.json; do echo $f; python -c "
 import json,sys

@@ -1,5 +1,5 @@
 mkdir -p gpurun_out
-python -m pytest tests/test_gpu_parity.py -m gpu -q -k "knn" > gpurun_out/r02f_pytest.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/r02f_pytest.log
+python -m pytest tests/test_gpu_parity.py tests/test_gpu_prune.py tests/test_gpu_fullsize.py tests/test_driver.py -m gpu -q -k "knn or prune or mspe or hygiene or cfg or penalty" > gpurun_out/r02f_pytest.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/r02f_pytest.log
 python bench.py --preset cfg5 --steps 1 --warmup 1 --no-cpu-baseline --no-exhaustive > gpurun_out/r02f_bench_cfg5.json 2> gpurun_out/r02f_bench_cfg5.err; echo "cfg5 rc=$?"
 python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-exhaustive > gpurun_out/r02f_bench_cfg3.json 2> gpurun_out/r02f_bench_cfg3.err; echo "cfg3 rc=$?"
 python bench.py --preset cfg4 --steps 1 --warmup 1 > gpurun_out/r02f_bench_cfg4.json 2> gpurun_out/r02f_bench_cfg4.err; echo "cfg4 rc=$?"; tail -5 gpurun_out/r02f_bench_cfg4.err
