@@ -372,7 +372,8 @@ def run_b200(args, preset):
                      x_next=x_next.tolist(), score=score, idx=idx, sizes=eng.counts.tolist(),
                      lml=eng.model["lml_host"].tolist(), shard_mode=fs["shard_mode"],
                      fit_async={k: (round(v, 4) if isinstance(v, float) else v) for k, v in fs.items()
-                                if k in ("lanes", "stolen", "given", "idle_s", "pairs_local")})
+                                if k in ("lanes", "stolen", "given", "idle_s", "pairs_local", "evals_per_rank",
+                                         "steps_per_rank", "stolen_per_rank", "loop_s_per_rank")})
         stats["_model"] = model
         return x_next
 

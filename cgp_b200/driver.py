@@ -188,7 +188,7 @@ class cGP_constrained(object):
                 X[:, j] = np.random.uniform(bounds[j, 0], bounds[j, 1], size=(self.N_PILOT, 1)).ravel()
         Y = np.zeros((X.shape[0], 1))
         for k in range(X.shape[0]):
-            Y[k, 0] = self.censor_function(self.f_truth(X[k, :].reshape(1, -1)))
+            Y[k, 0] = np.asarray(self.censor_function(self.f_truth(X[k, :].reshape(1, -1))), dtype=np.float64).reshape(-1)[0]
         dgm = self.f_Cluster(self.RND_SEED)
         model, labels = None, None
         fitted_n, fitted_labels = 0, None  # what `model` currently holds

@@ -399,12 +399,19 @@ class ClusterGPEngine:
         table = np.zeros((n_pairs, P + 3))
         for gid, (x, f, nfev, nit) in finished.items():
             table[gid, :P], table[gid, P], table[gid, P + 1], table[gid, P + 2] = x, f, nfev, nit
+        extra = dict(lanes=n_lanes, stolen=st["stolen"], given=st["given"], idle_s=st["idle_s"], pairs_local=len(mine))
         if ws > 1:  # every run finished on exactly one rank: the sum over ranks is the full table (exact: + 0.0)
             t = torch.from_numpy(table).to(self.device)
             torch.distributed.all_reduce(t)
             table = t.cpu().numpy()
-        return table, st["steps"], dict(lanes=n_lanes, stolen=st["stolen"], given=st["given"], idle_s=st["idle_s"],
-                                        pairs_local=len(mine))
+            mine_stats = torch.tensor([float(n_eval[0]), float(st["steps"]), float(st["stolen"]), st["loop_s"]],
+                                      dtype=torch.float64, device=self.device)
+            allst = torch.empty((ws, 4), dtype=torch.float64, device=self.device)
+            torch.distributed.all_gather_into_tensor(allst, mine_stats.reshape(1, 4))
+            a = allst.cpu().numpy()
+            extra.update(evals_per_rank=a[:, 0].astype(int).tolist(), steps_per_rank=a[:, 1].astype(int).tolist(),
+                         stolen_per_rank=a[:, 2].astype(int).tolist(), loop_s_per_rank=[round(v, 3) for v in a[:, 3]])
+        return table, st["steps"], extra
 
     def set_theta(self, theta):
         self.theta = np.asarray(theta, dtype=np.float64).reshape(self.C, self.P).copy()

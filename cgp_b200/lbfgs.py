@@ -191,82 +191,147 @@ class StealBoard:
     batch it is evaluated (the kernels are batch-invariant bit for bit), so the result is independent of the schedule.
     Nobody leaves the loop before all runs of all ranks are finished (global counter), so every request is answered.
 
+    All store traffic runs on a BACKGROUND THREAD (the c10d store calls release the GIL): it publishes this rank's load,
+    mirrors the other ranks' loads, the global finished-runs counter and this rank's request queue into plain attributes,
+    posts requests and fetches replies.  The optimiser loop only reads those attributes, so a store round trip (50-200 us,
+    ten of them per step boundary with 8 ranks: measured 1.6 ms per step, 0.37 s of a 2.07 s fit) never sits on the
+    critical path of the evaluations.
+
     Keys (under a per-fit prefix): load/<r> counter = active runs of rank r; done counter = finished runs (global);
     req/<v> counter = requests posted to victim v; who/<v>/<k> = "<thief>:<thief load>"; give/<v>/<k> = pickled runs."""
 
-    def __init__(self, store, prefix, rank, world, total_runs):
+    def __init__(self, store, prefix, rank, world, total_runs, period=2e-4):
+        import threading
+
         self.store, self.prefix, self.rank, self.world, self.total = store, prefix, rank, world, total_runs
-        self._load = 0
-        self._served = 0
-        self._pending = None  # (victim, k) of the one request in flight
-        self._last_poll = 0.0
         self.stolen = 0
         self.given = 0
+        # main thread -> I/O thread
+        self._load_target = 0      # active runs of this rank
+        self._done_add = 0         # finished runs not yet added to the global counter
+        self._want = None          # (victim, my_load): post a request
+        self._outbox = []          # (k, pickled runs): replies to publish
+        # I/O thread -> main thread
+        self._loads = [0] * world  # mirror of the load counters
+        self._done = 0             # mirror of the global counter
+        self._inbox = []           # (k, thief_load): requests to answer
+        self._reply = None         # runs received for the pending request
+        self._pending = None       # (victim, k) of the one request in flight
+        self._lock = threading.Lock()
+        self._stop = False
+        self._err = None
+        self._period = period
+        for r in range(world):     # make every key this thread reads exist
+            store.add(self._k(f"load/{r}"), 0)
+        store.add(self._k("done"), 0)
+        store.add(self._k(f"req/{rank}"), 0)
+        self._thread = threading.Thread(target=self._io_loop, daemon=True)
+        self._thread.start()
 
     def _k(self, name):
         return f"{self.prefix}/{name}"
 
+    # ------------------------------------------------------------------ I/O thread
+    def _io_loop(self):
+        import pickle
+        import time
+
+        store, published, served = self.store, 0, 0
+        load_keys = [self._k(f"load/{r}") for r in range(self.world)]
+        try:
+            while not self._stop:
+                with self._lock:
+                    target, add, self._done_add = self._load_target, self._done_add, 0
+                    out, self._outbox = self._outbox, []
+                    want, self._want = self._want, None
+                if target != published:
+                    store.add(self._k(f"load/{self.rank}"), target - published)
+                    published = target
+                for k, blob in out:
+                    store.set(self._k(f"give/{self.rank}/{k}"), blob)
+                self._done = store.add(self._k("done"), add)
+                cnt = store.add(self._k(f"req/{self.rank}"), 0)
+                while served < cnt:
+                    served += 1
+                    who = store.get(self._k(f"who/{self.rank}/{served}")).decode()
+                    with self._lock:
+                        self._inbox.append((served, int(who.split(":")[1])))
+                if self._pending is not None and self._reply is None:
+                    v, k = self._pending
+                    key = self._k(f"give/{v}/{k}")
+                    if store.check([key]):
+                        self._reply = pickle.loads(store.get(key))
+                elif want is not None and self._pending is None:
+                    v, my_load = want
+                    k = store.add(self._k(f"req/{v}"), 1)
+                    store.set(self._k(f"who/{v}/{k}"), f"{self.rank}:{my_load}")
+                    self._pending = (v, k)
+                vals = store.multi_get(load_keys)  # one round trip for all counters (ASCII integers)
+                self._loads = [int(v) if r != self.rank else -1 for r, v in enumerate(vals)]
+                if self._done >= self.total:
+                    break
+                time.sleep(self._period)
+        except BaseException as e:  # noqa: BLE001  (surface store failures in the optimiser loop instead of hanging)
+            self._err = e
+
+    def _check(self):
+        if self._err is not None:
+            raise RuntimeError("work-stealing store thread failed") from self._err
+
+    # ------------------------------------------------------------------ optimiser-loop side (never touches the store)
     def set_load(self, n):
-        if n != self._load:
-            self.store.add(self._k(f"load/{self.rank}"), n - self._load)
-            self._load = n
+        self._load_target = n
 
     def add_done(self, k):
         if k:
-            self.store.add(self._k("done"), k)
+            with self._lock:
+                self._done_add += k
 
     def all_done(self):
-        return self.store.add(self._k("done"), 0) >= self.total
+        self._check()
+        return self._done >= self.total
 
-    def maybe_request(self, my_load, min_interval=2e-3):
-        """Post a request to the busiest rank if it holds at least two runs more than this rank.  The loads of the other
-        ranks are read at most every `min_interval` seconds (one store round trip per rank)."""
-        if self._pending is not None:
+    def maybe_request(self, my_load):
+        """Ask the busiest rank for work if it holds at least two runs more than this rank."""
+        if self._pending is not None or self._want is not None:
             return
-        import time
-
-        now = time.perf_counter()
-        if now - self._last_poll < min_interval:
-            return
-        self._last_poll = now
-        loads = [self.store.add(self._k(f"load/{r}"), 0) if r != self.rank else -1 for r in range(self.world)]
+        loads = self._loads
         v = int(np.argmax(loads))
-        if loads[v] < my_load + 2:
-            return
-        k = self.store.add(self._k(f"req/{v}"), 1)
-        self.store.set(self._k(f"who/{v}/{k}"), f"{self.rank}:{my_load}")
-        self._pending = (v, k)
+        if loads[v] >= my_load + 2:
+            self._want = (v, my_load)
 
     def poll_reply(self):
         """-> list of stolen runs (possibly empty) when the pending request has been answered, else None."""
-        if self._pending is None:
+        runs = self._reply
+        if runs is None:
             return None
-        v, k = self._pending
-        key = self._k(f"give/{v}/{k}")
-        if not self.store.check([key]):
-            return None
-        import pickle
-
-        runs = pickle.loads(self.store.get(key))
+        self._reply = None
         self._pending = None
         self.stolen += len(runs)
         return runs
 
     def serve(self, ready, my_total):
-        """Victim side, called at a step boundary: answer every new request out of `ready` (list of runs, mutated)."""
-        cnt = self.store.add(self._k(f"req/{self.rank}"), 0)
-        while self._served < cnt:
-            self._served += 1
-            import pickle
+        """Victim side, called at a step boundary: answer every queued request out of `ready` (list of runs, mutated)."""
+        import pickle
 
-            who = self.store.get(self._k(f"who/{self.rank}/{self._served}")).decode()
-            thief_load = int(who.split(":")[1])
+        if not self._inbox:
+            return my_total
+        with self._lock:
+            reqs, self._inbox = self._inbox, []
+        for k, thief_load in reqs:
             give = max(0, min(len(ready), (my_total - thief_load) // 2))
             out = [ready.pop() for _ in range(give)]
             my_total -= give
             self.given += give
-            self.store.set(self._k(f"give/{self.rank}/{self._served}"), pickle.dumps(out, protocol=pickle.HIGHEST_PROTOCOL))
+            blob = pickle.dumps(out, protocol=pickle.HIGHEST_PROTOCOL)
+            with self._lock:
+                self._outbox.append((k, blob))
         return my_total
+
+    def close(self):
+        self._stop = True
+        self._thread.join(timeout=5)
+        self._check()
 
 
 def minimize_async(x0s, gids, lo, hi, submit, done, collect, n_lanes=2, lane_policy=None, board=None, max_evals=None,
@@ -284,6 +349,7 @@ def minimize_async(x0s, gids, lo, hi, submit, done, collect, n_lanes=2, lane_pol
     Returns (results {gid: (x, f, nfev, nit)} of the runs that FINISHED on this rank, stats dict)."""
     import time
 
+    t_start = time.perf_counter()
     runs_ready = []
     finished = {}
     n_steps = 0
@@ -337,15 +403,16 @@ def minimize_async(x0s, gids, lo, hi, submit, done, collect, n_lanes=2, lane_pol
                 board.add_done(new_done)
         # ---- work stealing: answer requests out of the ready pool, collect a reply, ask when short of work
         if board is not None:
-            total = board.serve(runs_ready, len(runs_ready) + in_flight) if runs_ready else len(runs_ready) + in_flight
+            total = len(runs_ready) + in_flight
+            if runs_ready or total == 0:
+                total = board.serve(runs_ready, total)
             got = board.poll_reply()
             if got:
                 runs_ready.extend(got)
                 total += len(got)
                 progressed = True
             board.set_load(total)
-            if progressed or total == 0:
-                board.maybe_request(total)
+            board.maybe_request(total)
         # ---- refill free lanes from the ready pool
         if runs_ready:
             active = len(runs_ready) + in_flight
@@ -369,11 +436,11 @@ def minimize_async(x0s, gids, lo, hi, submit, done, collect, n_lanes=2, lane_pol
                 break
             if board.all_done():
                 break
-            if board.serve([], 0):  # pragma: no cover  (serve returns the remaining total: 0)
-                pass
         if not progressed:
             t0 = time.perf_counter()
             time.sleep(poll_sleep)
             t_idle += time.perf_counter() - t0
-    return finished, dict(steps=n_steps, evals=n_evals, idle_s=t_idle,
+    if board is not None:
+        board.close()
+    return finished, dict(steps=n_steps, evals=n_evals, idle_s=t_idle, loop_s=time.perf_counter() - t_start,
                           stolen=0 if board is None else board.stolen, given=0 if board is None else board.given)
