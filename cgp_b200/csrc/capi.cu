@@ -465,9 +465,26 @@ static double flops_cube_third(const MatMeta* hm, int nm) {
     return f;
 }
 
+static int run_pipeline_body(HandleImpl* h, int kind, const double* X, const double* y, const double* theta, double alpha,
+                             int d, const Batch& b, const MatMeta* hm, double* lml, double* grad, int* info, cudaStream_t s);
+
 // assemble -> blocked Cholesky -> U = L^-T -> z, a, lml [-> K^-1 -> gradient].   hm: host copy of b.meta
+// A CUDA error in the middle of the three-stream section must not leave the internal streams running behind the
+// caller's back (or the handle muted for profiling): drain them before the error code is returned.
 static int run_pipeline(HandleImpl* h, int kind, const double* X, const double* y, const double* theta, double alpha, int d,
                         const Batch& b, const MatMeta* hm, double* lml, double* grad, int* info, cudaStream_t s) {
+    const int rc = run_pipeline_body(h, kind, X, y, theta, alpha, d, b, hm, lml, grad, info, s);
+    if (rc != 0) {
+        cudaStreamSynchronize(h->sc);
+        cudaStreamSynchronize(h->s2);
+        h->prof_mute = false;
+        h->pending_flops = 0.0;
+    }
+    return rc;
+}
+
+static int run_pipeline_body(HandleImpl* h, int kind, const double* X, const double* y, const double* theta, double alpha,
+                             int d, const Batch& b, const MatMeta* hm, double* lml, double* grad, int* info, cudaStream_t s) {
     const int nm = b.nm, T = b.Tmax;
     const size_t xs = xtile_smem(d);
     dim3 gl(b.ntl_max, nm);

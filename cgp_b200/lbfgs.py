@@ -238,6 +238,7 @@ class StealBoard:
 
         store, published, served = self.store, 0, 0
         load_keys = [self._k(f"load/{r}") for r in range(self.world)]
+        multi = hasattr(store, "multi_get")
         try:
             while not self._stop:
                 with self._lock:
@@ -266,8 +267,14 @@ class StealBoard:
                     k = store.add(self._k(f"req/{v}"), 1)
                     store.set(self._k(f"who/{v}/{k}"), f"{self.rank}:{my_load}")
                     self._pending = (v, k)
-                vals = store.multi_get(load_keys)  # one round trip for all counters (ASCII integers)
-                self._loads = [int(v) if r != self.rank else -1 for r, v in enumerate(vals)]
+                if multi:
+                    try:  # one round trip for all counters (ASCII integers)
+                        vals = [int(v) for v in store.multi_get(load_keys)]
+                    except (RuntimeError, NotImplementedError, ValueError):  # store without multi_get (FileStore ...)
+                        multi = False
+                if not multi:
+                    vals = [store.add(k, 0) for k in load_keys]
+                self._loads = [v if r != self.rank else -1 for r, v in enumerate(vals)]
                 if self._done >= self.total:
                     break
                 time.sleep(self._period)

@@ -1,4 +1,4 @@
-"""Timings of the other BASELINE.json configs on ONE B200 (bench.py's headline is config 3).
+"""Round-1 tool (superseded by `bench.py --preset cfg2|cfg4|cfg5`): timings of the other BASELINE.json configs on ONE B200.
     python tools/config_runs.py cfg1 | cfg2 | cfg5 [--m M] | cfg4 [--n N --m M]
 Data definitions: SURVEY.md §8d."""
 import json
@@ -27,44 +27,25 @@ def arg(name, default):
 
 
 def cfg2():
-    """Schaffer N2 2-D, N_PILOT=2000, DGM4 clusters (host), R=20, 64k candidates."""
+    """Schaffer N2 2-D, N_PILOT=2000, DGM4 clusters (host), R=20, 64k candidates (tools/workloads.py)."""
     import oracle
     from cgp_b200.plugins import DGM4
+    from tools import workloads as W
 
-    np.random.seed(123)
-    N, d, M, R = 2000, 2, 65536, 20
-    X = np.zeros((N, d))
-    for j in range(d):
-        X[:, j] = np.random.uniform(-100, 100, size=(N, 1)).ravel()
-    x, yy = X[:, 0], X[:, 1]
-    y = 0.5 + (np.sin(x * x - yy * yy) ** 2 - 0.5) / (1 + 0.001 * (x * x + yy * yy)) ** 2
+    X, y = W.cfg2_samples()
     t_cl = time.perf_counter()
     lab = DGM4.f_Cluster(123).fit_predict(np.concatenate([X, y[:, None]], axis=1))
-    lab = oracle.recode(oracle.merge_small_clusters(lab, d))
+    lab = oracle.recode(oracle.merge_small_clusters(lab, 2))
     t_cl = time.perf_counter() - t_cl
-    Q = np.random.default_rng(2024).uniform(-100, 100, size=(M, d))
-    return X, y, lab, Q, R, dict(host_clustering_s=t_cl)
+    return X, y, lab, W.cfg2_candidates(), 20, dict(host_clustering_s=t_cl)
 
 
 def cfg5():
-    """8-D, 64 clusters of n_c in [480, 544] (cells of a 2^6 split on x0..x5), R=32, 16M candidates."""
-    rng = np.random.default_rng(0)
-    C, d, R = 64, 8, 32
-    M = arg("--m", 16777216)
-    sizes = rng.integers(480, 545, size=C)
-    Xs, labs = [], []
-    for c in range(C):
-        x = rng.uniform(size=(sizes[c], d))
-        for b in range(6):
-            x[:, b] = 0.5 * x[:, b] + 0.5 * ((c >> b) & 1)
-        Xs.append(x)
-        labs.append(np.full(sizes[c], c))
-    X, lab = np.concatenate(Xs), np.concatenate(labs)
-    perm = rng.permutation(X.shape[0])
-    X, lab = X[perm], lab[perm]
-    y = lab % 7 + np.sin(2 * np.pi * X.sum(1) / 8) + 0.01 * rng.standard_normal(X.shape[0])
-    Q = np.random.default_rng(1).uniform(size=(M, d))
-    return X, y, lab, Q, R, {}
+    """8-D, 64 clusters of n_c in [480, 544], R=32, 16M candidates (tools/workloads.py)."""
+    from tools import workloads as W
+
+    X, y, lab, Q = W.cfg5(64, arg("--m", 16777216))
+    return X, y, lab, Q, 32, {}
 
 
 def run_fit_scan(name, X, y, lab, Q, R, extra):
