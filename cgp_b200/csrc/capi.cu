@@ -977,12 +977,25 @@ struct ScoreLayout {
     size_t o_perm, o_qs, o_sorted, o_hist, o_blkoff, o_coff, o_blkv, o_blkp, o_kstar, o_vpart, o_mraw, o_kmax, o_sel, o_cnt, o_lb, total;
 };
 
+static int64_t score_chunk_min() {
+    static const int64_t v = [] {
+        const char* e = getenv("CGP_SCORE_CHUNK_MIN");
+        return e ? (int64_t)atoll(e) : (int64_t)16384;
+    }();
+    return v;
+}
+#define CGP_FIRST_PRUNE_CHUNK 2048  // the first chunk of a pruned scan is scored exhaustively (no bound yet): keep it small
+
 static ScoreLayout score_layout(const int64_t* offs, int C, int d, int64_t m) {
     ScoreLayout L;
     L.npad_max = 0;
     for (int c = 0; c < C; ++c) L.npad_max = std::max<int64_t>(L.npad_max, pad_n(offs[c + 1] - offs[c]));
     L.Tmax = (int)(L.npad_max / CGP_TILE);
+    // candidates per chunk: a 1 GB cross-kernel block, but at least CGP_SCORE_CHUNK_MIN (16384) candidates as long as the
+    // block stays <= 8 GB: with giant clusters (configs[3]: n = 65536 -> 2048 candidates per GB) the survivors of the
+    // pruned scan are too few per chunk to fill the 128-candidate tiles of the variance contraction
     int64_t mch = ((int64_t)1 << 27) / std::max<int64_t>(L.npad_max, 1);
+    mch = std::max<int64_t>(mch, std::min<int64_t>(score_chunk_min(), ((int64_t)1 << 30) / std::max<int64_t>(L.npad_max, 1)));
     mch = std::max<int64_t>(CGP_TILE, std::min<int64_t>(mch, 65536));
     mch = mch / CGP_TILE * CGP_TILE;
     mch = std::min<int64_t>(mch, pad_n(std::max<int64_t>(m, 1)));
@@ -1057,6 +1070,7 @@ static int run_score(HandleImpl* h, int kind, const double* X, const int64_t* of
     const int P = d + 1;
     long long woff = 0;
     if (prune) KL(h, CLS_SCORE_FINISH, s, k_set_double<<<1, 1, 0, s>>>(lb, -INFINITY));
+    bool first_chunk = prune;
     for (int c = 0; c < C; ++c) {
         const int64_t n = offs[c + 1] - offs[c];
         const int64_t npad = pad_n(n);
@@ -1065,8 +1079,9 @@ static int run_score(HandleImpl* h, int kind, const double* X, const int64_t* of
         woff += npad * npad;
         const double* th = theta + (long long)c * P;
         const double* Xc = X + offs[c] * d;
-        for (long long p0 = hoff[c]; p0 < hoff[c + 1]; p0 += L.mch) {
-            const long long rows = std::min<long long>(L.mch, hoff[c + 1] - p0);
+        for (long long p0 = hoff[c], rows = 0; p0 < hoff[c + 1]; p0 += rows) {
+            rows = std::min<long long>(first_chunk ? std::min<long long>(L.mch, CGP_FIRST_PRUNE_CHUNK) : L.mch, hoff[c + 1] - p0);
+            first_chunk = false;
             const long long rows_pad = pad_n(rows);
             int rc = launch_cross(h, kind, Qs + p0 * d, rows, Xc, n, d, th, kstar, npad, rows_pad, npad, 0, 0.0, s);
             if (rc) return rc;
