@@ -492,6 +492,19 @@ def run_b200(args, preset):
         cpu["note"] = ("scikit-learn 1.9.0 / SciPy / OpenBLAS objects configured exactly as the reference does "
                        "(the arithmetic the reference delegates to) + oracle EI restatement")
         parity = parity_block(preset, Xw, yw, lw, Q_head, refvals, dev)
+    # fully MEASURED (nothing extrapolated) CPU comparison committed for configs[1]: the whole scikit-learn iteration on the
+    # host cores against this arm's line for the same preset (profiles/, produced by `--impl reference --preset cfg2 --measured`)
+    measured = None
+    try:
+        ref2 = json.load(open(os.path.join(ROOT, "profiles", "r02_bench_reference_cfg2_measured.json")))
+        gpu2 = json.load(open(os.path.join(ROOT, "profiles", "r02_bench_cfg2_1gpu.json")))
+        measured = {"workload": gpu2["config"]["workload"], "cpu_iteration_s": round(ref2["ms_per_step"] * 1e-3, 2),
+                    "cpu_cores": ref2["cpu_baseline"]["cores"], "b200_iteration_s": round(gpu2["ms_per_step"] * 1e-3, 4),
+                    "b200_e2e_iteration_s": round(gpu2["e2e"]["ms_per_step"] * 1e-3, 4),
+                    "same_selected_candidate": ref2["cpu_baseline"]["selected_idx"] == gpu2["selected"]["idx"],
+                    "source": "profiles/r02_bench_reference_cfg2_measured.json, profiles/r02_bench_cfg2_1gpu.json"}
+    except Exception:  # noqa: BLE001
+        pass
     line = {"metric": p["metric"], "value": M / step_s, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": {"workload": p["name"]},
@@ -501,7 +514,8 @@ def run_b200(args, preset):
             "e2e": {"value": M / e2e_s, "unit": UNIT,
                     "h2d_bytes_per_step": int(Q_pin.numel() * 8 + X.nbytes + y.nbytes + labels.nbytes),
                     "d2h_bytes_per_step": int((p["d"] + 2) * 8), "ms_per_step": e2e_s * 1e3},
-            "gpu_launches": gpu_launches, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
+            "gpu_launches": gpu_launches, "roofline": roofline, "cpu_baseline": cpu,
+            "cpu_comparison_fully_measured": measured, "clocks": clocks,
             "acq": "exact bound-pruned scan (public default)", "acq_exhaustive_scan": exhaustive,
             "acq_candidates_per_s": M / res["acq_s"], "lml_evals_per_fit_rank0": res["evals"],
             "lml_evals_committed": evals_file, "lockstep_per_fit": res["lockstep"], "shard_mode": res["shard_mode"], "fit_async_rank0": res["fit_async"],
