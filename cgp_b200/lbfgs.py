@@ -76,8 +76,7 @@ class _Run:
 
     def advance(self):
         """Run setulb until it asks for (f, g) at self.x (returns True) or terminates (returns False)."""
-        while True:
-            self.g = self.g.astype(np.float64)
+        while True:  # self.g is always a private float64 array (feed copies), so SciPy's per-iteration astype is not needed
             _lbfgsb.setulb(self.m, self.x, self.lo, self.hi, self.nbd, self.f, self.g, self.factr, self.pgtol, self.wa,
                            self.iwa, self.task, self.lsave, self.isave, self.dsave, self.maxls, self.ln_task)
             if self.task[0] == 3:
