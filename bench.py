@@ -396,13 +396,9 @@ def run_b200(args, preset):
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         return float(dt[0]), float(dt[1])
 
-    for i in range(args.warmup):
-        # the last warm-up step runs with per-launch event timing on, so that the event pool of the C library is
-        # created here and not inside the timed region
-        _lib.profile_enable(2 if i == args.warmup - 1 else 0, local)
-        step(Q_dev, False)
-    _lib.profile_enable(False, local)
-    # fp64 tensor peak measured here (cuBLAS DGEMM through torch; MEASURED_PEAKS.json has bf16 only)
+    # fp64 tensor peak measured here (cuBLAS DGEMM through torch; MEASURED_PEAKS.json has bf16 only) BEFORE the warm-up
+    # steps, so that the timed region follows the warm-up directly (the probe's buffers and empty_cache would otherwise
+    # make the first timed step pay cudaMalloc for every workspace again)
     torch.cuda.empty_cache()
     A = torch.randn((8192, 8192), dtype=torch.float64, device=dev)
     Bm = torch.randn((8192, 8192), dtype=torch.float64, device=dev)
@@ -419,6 +415,12 @@ def run_b200(args, preset):
     del A, Bm, Cm
     torch.cuda.empty_cache()
 
+    for i in range(args.warmup):
+        # the last warm-up step runs with per-launch event timing on, so that the event pool of the C library is
+        # created here and not inside the timed region
+        _lib.profile_enable(2 if i == args.warmup - 1 else 0, local)
+        step(Q_dev, False)
+    _lib.profile_enable(False, local)
     sampler = ClockSampler(local)
     _lib.profile_read(reset=True, device=local)
     _lib.profile_enable(2, local)  # events around the large kernels only; every launch is still counted
