@@ -120,6 +120,31 @@ __device__ __forceinline__ void ktc_insert(float (&v)[KTC_KP], int (&ix)[KTC_KP]
     }
 }
 
+// k-th smallest (k <= 3) of the values the four lanes of a query row have kept: every lane contributes its three
+// smallest (sorted); two xor-shuffle rounds inside the 4-lane group merge them (branch-free insertion of the partner's
+// triple), after which every lane of the group holds the row's three smallest.  All 32 lanes must call it.
+__device__ __forceinline__ float ktc_row_kth(const float (&v)[KTC_KP], int k) {
+    float a0 = v[0], a1 = v[1], a2 = v[2];
+#pragma unroll
+    for (int m = 1; m <= 2; m <<= 1) {
+        const float b0 = __shfl_xor_sync(0xffffffffu, a0, m);
+        const float b1 = __shfl_xor_sync(0xffffffffu, a1, m);
+        const float b2 = __shfl_xor_sync(0xffffffffu, a2, m);
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            const float x = q == 0 ? b0 : (q == 1 ? b1 : b2);
+            a2 = fminf(a2, x);
+            float lo = fminf(a1, a2);
+            a2 = fmaxf(a1, a2);
+            a1 = lo;
+            lo = fminf(a0, a1);
+            a1 = fmaxf(a0, a1);
+            a0 = lo;
+        }
+    }
+    return k == 1 ? a0 : (k == 2 ? a1 : a2);
+}
+
 // ---- main kernel --------------------------------------------------------------------------------------------------
 // grid ceil(M / 128), block 256.  Dynamic smem: 2 stages x (KTC_TILE x DP float2 + KTC_TILE float) + merge area
 // 8 warps x 16 rows x 16 entries x (float + int).
@@ -175,6 +200,34 @@ k_knn_tc(const float2* __restrict__ Xp, const float* __restrict__ xn, const floa
         v0[s] = v1[s] = INFINITY;
         i0[s] = i1[s] = -1;
     }
+    // Row-wide cut.  A lane only has to keep points that can still be survivors, i.e. s~ <= tau_final + 2 eps; tau_final is
+    // at most the k-th smallest s~ the whole ROW (its four lanes) has kept so far, so everything above
+    // rc = (k-th smallest of the row so far) + 2 eps' (eps' >= eps_q) is dropped at once.  The row sees four times the
+    // points of a lane and uses its k-th instead of the lane's (k+1)-th value, which cuts the number of list insertions
+    // (the slow path of this loop) ~4.5x.  rc is refreshed after every insertion (two xor-shuffle rounds in the 4-lane group).
+    float e2r0, e2r1;  // 2 eps' of rows g and g + 8
+    {
+        float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int p = ks * 8 + t + ((e & 2) ? 4 : 0);
+                const float a = fabsf(__uint_as_float(ahi[ks][e])) + fabsf(__uint_as_float(alo[ks][e]));  // >= |2 q_p|
+                if (e & 1)
+                    s1 += a * stats[p];
+                else
+                    s0 += a * stats[p];
+            }
+        s0 += __shfl_xor_sync(0xffffffffu, s0, 1);
+        s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
+        s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
+        s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+        e2r0 = 2.f * 1.001f * KTC_EPS_SCALE * (stats[DP] + s0 * 1.0000005f);
+        e2r1 = 2.f * 1.001f * KTC_EPS_SCALE * (stats[DP] + s1 * 1.0000005f);
+    }
+    float rc0 = INFINITY, rc1 = INFINITY;  // row cuts
+    float h0 = INFINITY, h1 = INFINITY;    // hit thresholds = min(lane's largest kept value, row cut)
 
     const int ntiles = npad / KTC_TILE;
     ktc_load_stage<DP>(ktc_smem, Xp, xn, 0, tid);
@@ -203,13 +256,17 @@ k_knn_tc(const float2* __restrict__ Xp, const float* __restrict__ xn, const floa
             }
             // almost never taken after the first tiles: one warp-uniform branch keeps the (long, predicated) insertion
             // code out of the steady-state instruction stream
-            const bool hit = fminf(c[0], c[1]) < v0[KTC_KP - 1] || fminf(c[2], c[3]) < v1[KTC_KP - 1];
+            const bool hit = fminf(c[0], c[1]) < h0 || fminf(c[2], c[3]) < h1;
             if (__any_sync(0xffffffffu, hit)) {
                 const int j = tl * KTC_TILE + j8 * 8 + 2 * t;
-                if (c[0] < v0[KTC_KP - 1]) ktc_insert(v0, i0, c[0], j);
-                if (c[1] < v0[KTC_KP - 1]) ktc_insert(v0, i0, c[1], j + 1);
-                if (c[2] < v1[KTC_KP - 1]) ktc_insert(v1, i1, c[2], j);
-                if (c[3] < v1[KTC_KP - 1]) ktc_insert(v1, i1, c[3], j + 1);
+                if (c[0] < v0[KTC_KP - 1] && c[0] < rc0) ktc_insert(v0, i0, c[0], j);
+                if (c[1] < v0[KTC_KP - 1] && c[1] < rc0) ktc_insert(v0, i0, c[1], j + 1);
+                if (c[2] < v1[KTC_KP - 1] && c[2] < rc1) ktc_insert(v1, i1, c[2], j);
+                if (c[3] < v1[KTC_KP - 1] && c[3] < rc1) ktc_insert(v1, i1, c[3], j + 1);
+                rc0 = ktc_row_kth(v0, k) + e2r0;
+                rc1 = ktc_row_kth(v1, k) + e2r1;
+                h0 = fminf(v0[KTC_KP - 1], rc0);
+                h1 = fminf(v1[KTC_KP - 1], rc1);
             }
         }
         __syncthreads();
