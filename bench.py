@@ -203,12 +203,10 @@ def cpu_sample(preset, X, y, labels, Q, evals_per_fit, m_sub=8192, n_eval=3):
                 s_per_lml_grad_eval=s_eval, n_lml_grad_evals_timed=n_eval, knn_s=t_knn, predict_ei_s=t_pred,
                 fit_s_extrapolated=fit_s, acq_s_extrapolated=acq_s, iteration_s_extrapolated=fit_s + acq_s,
                 evals_per_fit=evals_per_fit,
-                sample=(f"{n_eval} sklearn log_marginal_likelihood(eval_gradient=True) at n_c={n_s}"
-                        + (f" (cluster of {n_full} truncated: K_gradient does not fit; scaled by (n/{n_s})^3)" if scaled else "")
-                        + f" x {evals_per_fit} evaluations/fit (profiles/fit_evals.json, measured by the B200 arm, same SciPy "
-                        f"L-BFGS-B) + KNeighborsClassifier.predict / GPR.predict(return_std) / EI on {m_sub} of {p['M']} "
-                        "candidates, extrapolated linearly; the reference itself runs ONE trust-constr EI search per "
-                        "cluster instead of a dense scan, so this is the CPU cost of the SAME dense-scan iteration"))
+                sample=(f"{n_eval} sklearn LML+grad evals at n_c={n_s}"
+                        + (f" (of {n_full}: K_gradient does not fit; x (n/{n_s})^3)" if scaled else "")
+                        + f" x {evals_per_fit} evals/fit (profiles/fit_evals.json) + kNN/predict/EI on {m_sub} of {p['M']} "
+                        "candidates, extrapolated; CPU cost of the same dense-scan iteration (DESIGN.md 7)"))
     vals = dict(theta=theta + 0.01, theta_fit=theta, lml=float(val[0]), grad=np.asarray(val[1]), labels=lab,
                 mean=np.asarray(mu).reshape(-1), std=np.asarray(sd), ei=ei, c0=c0, m_sub=m_sub, truncated=scaled, n_s=n_s)
     return base, vals
@@ -461,7 +459,7 @@ def run_b200(args, preset):
     roof_all = {}
     for k, v in prof.items():
         if v["ms"] > 0 and v["flops"] > 0:
-            roof_all[k] = {"ms": round(v["ms"], 2), "timed_launches": v["timed"], "launches": v["launches"],
+            roof_all[k] = {"ms": round(v["ms"], 1), "timed": v["timed"],
                            "tflops": round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 2),
                            "frac": round(v["flops"] / (v["ms"] * 1e-3) / 1e12 / fp64_peak, 3),
                            "share_of_step": round(v["ms"] * 1e-3 / t_dev, 3)}
@@ -476,23 +474,22 @@ def run_b200(args, preset):
             traffic = json.load(open(tpath)).get(top)
         roofline = {"bound": "tensor", "kernel": "k_" + top, "achieved": roof_all[top]["tflops"], "peak": round(fp64_peak, 2),
                     "unit": "TFLOP/s", "frac": roof_all[top]["frac"], "traffic": traffic,
-                    "peak_source": "cuBLAS DGEMM 8192^3 fp64 measured in this run (MEASURED_PEAKS.json has no fp64 entry)",
-                    "choice": "class with the largest exclusive time in the timed region; batches <= CGP_FORK_MAX matrices "
-                              "(three-stream schedule) are counted but not timed",
+                    "peak_source": "cuBLAS DGEMM 8192^3 measured in-run",
                     "classes": roof_all,
-                    "step": {"algorithmic_flops": step_flops, "note": "n_c^3 per LML+grad evaluation (potrf + inverse + K^-1) "
-                             "+ 2/3 n_c^3 per final factorisation, rank 0; over the whole iteration incl. host L-BFGS-B and the scan",
+                    "step": {"algorithmic_flops": step_flops,
                              "tflops": round(step_flops / step_s / 1e12, 2), "frac": round(step_flops / step_s / 1e12 / fp64_peak, 3),
                              "fit_only_frac": round(step_flops / res["fit_s"] / 1e12 / fp64_peak, 3)}}
     gpu_launches = int(sum(v["launches"] for v in prof.values()))
     cpu = parity = None
+    detail_cpu = {}
     evals_file = committed_evals(preset)
     if world == 1 and not args.no_cpu_baseline:
         Xw, yw, lw, _ = make_workload(preset, M=0)
         cpu, refvals = cpu_sample(preset, Xw, yw, lw, Q_head, res["evals"])
         cpu["kind"] = "port"
-        cpu["note"] = ("scikit-learn 1.9.0 / SciPy / OpenBLAS objects configured exactly as the reference does "
-                       "(the arithmetic the reference delegates to) + oracle EI restatement")
+        for k in ("host_cpus", "knn_s", "predict_ei_s", "n_lml_grad_evals_timed", "fit_s_extrapolated", "acq_s_extrapolated",
+                  "evals_per_fit"):
+            detail_cpu[k] = cpu.pop(k, None)  # kept in the detail file, not in the one-line summary
         parity = parity_block(preset, Xw, yw, lw, Q_head, refvals, dev)
     # fully MEASURED (nothing extrapolated) CPU comparison committed for configs[1]: the whole scikit-learn iteration on the
     # host cores against this arm's line for the same preset (profiles/, produced by `--impl reference --preset cfg2 --measured`)
@@ -500,11 +497,11 @@ def run_b200(args, preset):
     try:
         ref2 = json.load(open(os.path.join(ROOT, "profiles", "r02_bench_reference_cfg2_measured.json")))
         gpu2 = json.load(open(os.path.join(ROOT, "profiles", "r02_bench_cfg2_1gpu.json")))
-        measured = {"workload": gpu2["config"]["workload"], "cpu_iteration_s": round(ref2["ms_per_step"] * 1e-3, 2),
-                    "cpu_cores": ref2["cpu_baseline"]["cores"], "b200_iteration_s": round(gpu2["ms_per_step"] * 1e-3, 4),
-                    "b200_e2e_iteration_s": round(gpu2["e2e"]["ms_per_step"] * 1e-3, 4),
-                    "same_selected_candidate": ref2["cpu_baseline"]["selected_idx"] == gpu2["selected"]["idx"],
-                    "source": "profiles/r02_bench_reference_cfg2_measured.json, profiles/r02_bench_cfg2_1gpu.json"}
+        measured = {"workload": "configs[1]", "cpu_s": round(ref2["ms_per_step"] * 1e-3, 2),
+                    "cpu_cores": ref2["cpu_baseline"]["cores"], "b200_s": round(gpu2["ms_per_step"] * 1e-3, 4),
+                    "b200_e2e_s": round(gpu2["e2e"]["ms_per_step"] * 1e-3, 4),
+                    "same_selected": ref2["cpu_baseline"]["selected_idx"] == gpu2["selected"]["idx"],
+                    "source": "profiles/r02_bench_{reference_cfg2_measured,cfg2_1gpu}.json"}
     except Exception:  # noqa: BLE001
         pass
     line = {"metric": p["metric"], "value": M / step_s, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -518,18 +515,16 @@ def run_b200(args, preset):
                     "d2h_bytes_per_step": int((p["d"] + 2) * 8), "ms_per_step": e2e_s * 1e3},
             "gpu_launches": gpu_launches, "roofline": roofline, "cpu_baseline": cpu,
             "cpu_comparison_fully_measured": measured, "clocks": clocks,
-            "acq": "exact bound-pruned scan (public default)", "acq_exhaustive_scan": exhaustive,
+            "acq": "exact pruned scan (default)", "acq_exhaustive_scan": exhaustive,
             "acq_candidates_per_s": M / res["acq_s"], "lml_evals_per_fit_rank0": res["evals"],
             "lml_evals_committed": evals_file, "lockstep_per_fit": res["lockstep"], "shard_mode": res["shard_mode"], "fit_async_rank0": res["fit_async"],
-            "fit_eval_wall_s": round(res["eval_s"], 4), "fit_optimizer_host_s": round(res["opt_host_s"], 4),
-            "wall_s_per_step": t_wall / args.steps,
-            "parallelism": f"(cluster, restart) runs + candidates sharded over {world} GPU(s)",
-            "l2": "working set (factor workspaces of tens of GB, 1 GB K* chunks) >> 126 MB L2; no flush needed",
-            "timing": "CUDA events around K whole steps, barrier+synchronize both sides, max over ranks"}
+            "fit_optimizer_host_s": round(res["opt_host_s"], 4),
+            "l2": "working set >> 126 MB L2, no flush"}
     emit(line)
     detail = {"preset": preset, "n_gpus": world, "nfev_per_pair_rank0_sorted": res["nfev_sorted"],
               "evals_per_cluster_rank0": res["evals_per_cluster"], "sizes": res["sizes"], "lml": res["lml"],
-              "kernel_classes": prof}
+              "kernel_classes": prof, "cpu_baseline_detail": detail_cpu, "fit_eval_wall_s": res["eval_s"],
+              "wall_s_per_step": t_wall / args.steps}
     try:
         os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
         json.dump(detail, open(os.path.join(ROOT, "gpurun_out", f"bench_detail_{preset}_n{world}.json"), "w"))
