@@ -254,6 +254,7 @@ class StealBoard:
                 while served < cnt:
                     served += 1
                     who = store.get(self._k(f"who/{self.rank}/{served}")).decode()
+                    self._drop(self._k(f"who/{self.rank}/{served}"))
                     with self._lock:
                         self._inbox.append((served, int(who.split(":")[1])))
                 if self._pending is not None and self._reply is None:
@@ -261,6 +262,7 @@ class StealBoard:
                     key = self._k(f"give/{v}/{k}")
                     if store.check([key]):
                         self._reply = pickle.loads(store.get(key))
+                        self._drop(key)  # the blob (~15 KB per run) must not pile up in the store of a long BO loop
                 elif want is not None and self._pending is None:
                     v, my_load = want
                     k = store.add(self._k(f"req/{v}"), 1)
@@ -279,6 +281,12 @@ class StealBoard:
                 time.sleep(self._period)
         except BaseException as e:  # noqa: BLE001  (surface store failures in the optimiser loop instead of hanging)
             self._err = e
+
+    def _drop(self, key):
+        try:
+            self.store.delete_key(key)
+        except Exception:  # noqa: BLE001  (stores without delete_key: the key simply stays)
+            pass
 
     def _check(self):
         if self._err is not None:
