@@ -2,8 +2,10 @@
 
 The path shards on its natural units (REF/cGP/cGP_parallel.py:396-407 is the precedent for
 "clusters are independent"):
-  * fit: the C*(R+1) (cluster, restart) L-BFGS-B problems are dealt round-robin to ranks; the only exchange
-    is one all-gather of each rank's per-pair (theta*, -lml) rows (a few KB);
+  * fit: the C*(R+1) (cluster, restart) L-BFGS-B runs are dealt to ranks; in the default "async" mode
+    (engine.fit, lbfgs.minimize_async / StealBoard) every rank owns whole runs, idle ranks steal ready runs over
+    the c10d store, and the only collective is one all-reduce of the per-run (theta*, -lml) table (a few KB);
+    the helpers below serve the "static" mode (deal once, one all-gather of each rank's rows);
   * scoring: candidates are split into contiguous equal shards; the only exchange is one all-gather of each
     rank's (best score, candidate index, cluster) and one broadcast of the selected point.
 All helpers work on CPU tensors with the gloo backend too (tests/test_dist_gloo.py).
